@@ -1,0 +1,170 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE.
+
+Build-container only: imports the unmodified reference package from
+``/root/reference`` (behind empty ``matplotlib`` / ``h5py`` stub modules, which
+the hot path never calls) and records small input/output vectors.  The GPU box
+has no ``/root/reference``; tests there read the committed ``*.pt`` files.
+
+    python tests/golden/make_golden.py
+
+What is recorded (torch 2.11.0 CPU):
+  kat_a.pt       FNO3d forward, recipe of SURVEY.md section 4 (KAT-A)
+  kat_b.pt       SpectralConv3d forward (KAT-B)
+  fno3d_odd.pt   FNO3d with odd grid sizes, T_out = 2*T_in (r=2 unfold) and train-mode BN
+  rollout.pt     eval.py:297-326 executed verbatim (source lines exec'd) on the
+                 reference FNO3d + GaussianNormalizer: plain (C_in==C_out),
+                 controlled (C_in = C_out+2) and RangeNormalizer cases
+  spectral2d.pt  MWT sparseKernelFT2d spectral math (2-D semantics pin)
+"""
+import os
+import sys
+import textwrap
+import types
+
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "h5py"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from realpdebench.model.fno import FNO3d, SpectralConv3d
+    from realpdebench.data.data_normalizer import GaussianNormalizer, RangeNormalizer
+    from realpdebench.utils.metrics import mse_loss
+    return FNO3d, SpectralConv3d, GaussianNormalizer, RangeNormalizer, mse_loss
+
+
+def randomize_bn(m, seed=123):
+    g = torch.Generator().manual_seed(seed)
+    for bn in m.bns:
+        c = bn.weight.numel()
+        bn.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.weight.data.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.bias.data.copy_(torch.randn(c, generator=g) * 0.1)
+
+
+def sd_of(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def eval_loop_source():
+    """The reference's rollout body, eval.py:297-326, as an exec-able string."""
+    with open(os.path.join(REF, "realpdebench", "eval.py")) as f:
+        lines = f.readlines()
+    body = "".join(lines[296:326])  # 1-based 297..326
+    assert "b = input.size(0)" in lines[296] and "postprocess(input, target)" in lines[325]
+    return textwrap.dedent(body)
+
+
+def run_reference_rollout(model, normalizer, input, target, n_auto, mse_loss):
+    ns = dict(torch=torch, model=model, data_normalizer=normalizer, input=input, target=target,
+              args=types.SimpleNamespace(N_autoregressive=n_auto), mse_loss=mse_loss,
+              normalized_test_loss=0.0)
+    with torch.no_grad():
+        exec(eval_loop_source(), ns)
+    return ns["pred"], ns["target"], ns["normalized_test_loss"], ns["preds"]
+
+
+def main():
+    torch.set_num_threads(1)
+    FNO3d, SpectralConv3d, GaussianNormalizer, RangeNormalizer, mse_loss = import_reference()
+
+    # ---- KAT-A -----------------------------------------------------------
+    torch.manual_seed(0)
+    m = FNO3d(2, 4, 4, 2, 8, (10, 16, 32, 3), (10, 16, 32, 3)).eval()
+    randomize_bn(m)
+    torch.manual_seed(1)
+    x = torch.randn(2, 10, 16, 32, 3)
+    with torch.no_grad():
+        y = m(x)
+    print("KAT-A", y.sum().item(), y.abs().sum().item(), y[0, 0, 0, 0].tolist())
+    torch.save(dict(sd=sd_of(m), x=x, y=y, ctor=(2, 4, 4, 2, 8, (10, 16, 32, 3), (10, 16, 32, 3))),
+               os.path.join(HERE, "kat_a.pt"))
+
+    # ---- KAT-B -----------------------------------------------------------
+    torch.manual_seed(2)
+    s = SpectralConv3d(4, 5, 2, 3, 4)
+    torch.manual_seed(3)
+    z = torch.randn(2, 4, 9, 10, 12)
+    with torch.no_grad():
+        o = s(z)
+    print("KAT-B", o.sum().item(), o.abs().sum().item(), o[0, 0, 0, 0, :3].tolist())
+    torch.save(dict(w=[getattr(s, f"weights{k}").detach().clone() for k in (1, 2, 3, 4)], z=z, o=o),
+               os.path.join(HERE, "kat_b.pt"))
+
+    # ---- odd sizes, r = 2, train-mode BN -----------------------------------
+    torch.manual_seed(10)
+    m = FNO3d(3, 3, 2, 3, 6, (5, 9, 7, 2), (10, 9, 7, 2))
+    randomize_bn(m, 77)
+    torch.manual_seed(11)
+    x = torch.randn(3, 5, 9, 7, 2)
+    sd0 = sd_of(m)
+    with torch.no_grad():
+        y_eval = m.eval()(x)
+        y_train = m.train()(x)
+    torch.save(dict(sd=sd0, sd_after_train=sd_of(m), x=x, y_eval=y_eval, y_train=y_train,
+                    ctor=(3, 3, 2, 3, 6, (5, 9, 7, 2), (10, 9, 7, 2))),
+               os.path.join(HERE, "fno3d_odd.pt"))
+
+    # ---- rollout, reference eval.py lines executed verbatim -------------------
+    cases = {}
+    for name, c_in, c_out, kind in (("plain", 3, 3, "gaussian"), ("controlled", 5, 3, "gaussian"),
+                                    ("range", 3, 3, "range")):
+        torch.manual_seed(20)
+        m = FNO3d(2, 3, 4, 2, 8, (4, 8, 12, c_in), (4, 8, 12, c_out)).eval()
+        randomize_bn(m, 5)
+        g = torch.Generator().manual_seed(4321)
+        if kind == "gaussian":
+            n = object.__new__(GaussianNormalizer)
+            n.device = "cpu"
+            n.mean_inputs, n.std_inputs = torch.randn(c_in, generator=g) * 0.1, torch.rand(c_in, generator=g) + 0.5
+            n.mean_targets, n.std_targets = torch.randn(c_out, generator=g) * 0.1, torch.rand(c_out, generator=g) + 0.5
+            stats = dict(mean_inputs=n.mean_inputs, std_inputs=n.std_inputs,
+                         mean_targets=n.mean_targets, std_targets=n.std_targets)
+        else:
+            n = object.__new__(RangeNormalizer)
+            n.device = "cpu"
+            n.max_inputs, n.max_targets = torch.rand(c_in, generator=g) + 1.0, torch.rand(c_out, generator=g) + 1.0
+            stats = dict(max_inputs=n.max_inputs, max_targets=n.max_targets)
+        torch.manual_seed(21)
+        n_auto = 3
+        inp = torch.randn(2, 4, 8, 12, c_in)
+        tgt = torch.randn(2, 4 * n_auto, 8, 12, c_out)
+        tgt[..., -1] = 0  # real-data convention: unmeasured pressure channel is all zero (fluid_dataset.py:357-359)
+        pred, tgt_dn, loss, preds = run_reference_rollout(m, n, inp, tgt, n_auto, mse_loss)
+        print("rollout", name, pred.shape, loss)
+        cases[name] = dict(sd=sd_of(m), ctor=(2, 3, 4, 2, 8, (4, 8, 12, c_in), (4, 8, 12, c_out)), kind=kind,
+                           stats=stats, input=inp, target=tgt, n_auto=n_auto, pred=pred, target_dn=tgt_dn,
+                           loss=loss, states=[p.clone() for p in preds])
+    torch.save(cases, os.path.join(HERE, "rollout.pt"))
+
+    # ---- 2-D spectral semantics: MWT sparseKernelFT2d -------------------------
+    from realpdebench.model.MWT_libs.models import sparseKernelFT2d
+    torch.manual_seed(30)
+    k, c, alpha = 2, 2, 5  # channels = c*k^2 = 8, modes = 5
+    sk = sparseKernelFT2d(k, alpha, c)
+    ch = c * k * k
+    with torch.no_grad():
+        sk.Lo.weight.copy_(torch.eye(ch))
+        sk.Lo.bias.zero_()
+        xx = torch.randn(2, 14, 18, c, k * k)
+        # forward ends with relu -> Lo(identity); the spectral map S is linear, so
+        # relu(S x) - relu(S(-x)) = S x recovers it from the unmodified module.
+        yy = sk(xx) - sk(-xx)
+    torch.save(dict(w1=sk.weights1.detach().clone(), w2=sk.weights2.detach().clone(),
+                    x=xx.view(2, 14, 18, ch).permute(0, 3, 1, 2).contiguous(),
+                    y=yy.view(2, 14, 18, ch).permute(0, 3, 1, 2).contiguous()),
+               os.path.join(HERE, "spectral2d.pt"))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.pt,
+written by tests/golden/make_golden.py) and the KATs of SURVEY.md section 4."""
+import pytest
+import torch
+
+from oracle import fno_oracle as O
+
+TOL = 2e-6  # same torch build, same ops; slack only for thread-count dependent reductions
+
+
+def test_kat_a_values_and_golden(golden):
+    g = golden("kat_a.pt")
+    y = O.fno3d_forward(g["sd"], g["x"], g["ctor"][6])
+    assert O.rel_l2(y, g["y"]) < TOL
+    # SURVEY section 4, KAT-A
+    assert abs(y.sum().item() - (-1280.620483)) < 2e-3
+    assert abs(y.abs().sum().item() - 2978.605713) < 2e-3
+    assert torch.allclose(y[0, 0, 0, 0], torch.tensor([-0.16739486, 0.09012541, -0.03944759]), atol=1e-6)
+    assert torch.allclose(y[1, 9, 15, 31], torch.tensor([-0.18006754, 0.08267292, -0.04100807]), atol=1e-6)
+
+
+def test_kat_a_init_order_reproduces_reference_weights(golden):
+    g = golden("kat_a.pt")
+    m1, m2, m3, L, width, s_in, s_out = g["ctor"]
+    torch.manual_seed(0)
+    sd = O.init_state(3, (m1, m2, m3), L, width, s_in, s_out)
+    O.randomize_bn(sd, 123)
+    assert set(sd) == set(g["sd"])
+    for k, v in g["sd"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+        assert torch.equal(sd[k], v), k
+
+
+def test_kat_b(golden):
+    g = golden("kat_b.pt")
+    o = O.spectral_conv3d(g["z"], *g["w"])
+    assert o.shape == (2, 5, 9, 10, 12)
+    assert O.rel_l2(o, g["o"]) < TOL
+    assert abs(o.sum().item() - 8.836092) < 1e-4
+    assert abs(o.abs().sum().item() - 259.263184) < 1e-3
+    assert torch.allclose(o[0, 0, 0, 0, :3], torch.tensor([0.03007768, 0.02350261, 0.00696487]), atol=1e-7)
+
+
+def test_odd_sizes_r2_and_train_mode(golden):
+    g = golden("fno3d_odd.pt")
+    s_out = g["ctor"][6]
+    assert O.rel_l2(O.fno3d_forward(g["sd"], g["x"], s_out), g["y_eval"]) < TOL
+    sd = {k: v.clone() for k, v in g["sd"].items()}
+    y = O.fno3d_forward(sd, g["x"], s_out, training=True)
+    assert O.rel_l2(y, g["y_train"]) < TOL
+    for i in range(3):  # running stats updated like nn.BatchNorm3d in train mode
+        for k in ("running_mean", "running_var"):
+            assert torch.allclose(sd[f"bns.{i}.{k}"], g["sd_after_train"][f"bns.{i}.{k}"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", ["plain", "controlled", "range"])
+def test_rollout_matches_reference_eval_loop(golden, case):
+    g = golden("rollout.pt")[case]
+    norm = O.Normalizer(g["kind"], **g["stats"])
+    fwd = lambda x: O.fno3d_forward(g["sd"], x, g["ctor"][6])
+    pred, tgt, loss, states = O.rollout(fwd, norm, g["input"], g["target"], g["n_auto"])
+    assert pred.shape == g["pred"].shape
+    assert O.rel_l2(pred, g["pred"]) < 1e-5  # 3 chained steps
+    assert O.rel_l2(tgt, g["target_dn"]) < TOL
+    assert abs(loss - g["loss"]) < 1e-5 * max(1.0, abs(g["loss"]))
+    assert len(states) == g["n_auto"] + 1
+    # teacher-forced: every step individually matches the reference state
+    _, _, _, st = O.rollout(fwd, norm, g["input"], g["target"], g["n_auto"], teacher=g["states"])
+    for a, b in zip(st, g["states"]):
+        assert O.rel_l2(a, b) < TOL
+
+
+def test_spectral2d_matches_mwt_kernel(golden):
+    g = golden("spectral2d.pt")
+    y = O.spectral_conv2d(g["x"], g["w1"], g["w2"])
+    assert O.rel_l2(y, g["y"]) < 1e-5  # golden is a difference of two relu'd fp32 results
+
+
+def test_irfftn_semantics_f5():
+    """irfftn == irfft_W(ifft_H(ifft_T(.))) on a non-Hermitian spectrum."""
+    torch.manual_seed(0)
+    s = torch.randn(2, 3, 6, 7, 5, dtype=torch.cfloat)
+    a = torch.fft.irfftn(s, s=(6, 7, 8))
+    b = torch.fft.irfft(torch.fft.ifft(torch.fft.ifft(s, dim=-3), dim=-2), n=8, dim=-1)
+    assert O.rel_l2(a, b) < 1e-6
+
+
+def test_fno2d_is_fno3d_with_time_folded():
+    """The frozen FNO-2D definition: shape/ordering contract and linear-lift consistency."""
+    torch.manual_seed(4)
+    s_in, s_out = (3, 10, 12, 2), (3, 10, 12, 2)
+    sd = O.init_state(2, (4, 5), 2, 8, s_in, s_out)
+    O.randomize_bn(sd)
+    assert sd["fc0.weight"].shape == (8, 3 * 2 + 2)
+    assert sd["fc2.weight"].shape == (3 * 2, 128)
+    assert sd["spectral_convs.0.weights2"].shape == (8, 8, 4, 5)
+    x = torch.randn(2, *s_in)
+    y = O.fno2d_forward(sd, x, s_out)
+    assert y.shape == (2, *s_out)
+    y64 = O.fno2d_forward({k: (v.double() if v.is_floating_point() else v.to(torch.cdouble) if v.is_complex() else v)
+                           for k, v in sd.items()}, x.double(), s_out)
+    assert O.rel_l2(y, y64) < 1e-5
