@@ -1,0 +1,171 @@
+/*
+ * b200fno — C ABI of the B200-native FNO forward / rollout engine.
+ *
+ * Drop-in boundary for the RealPDEBench FNO hot path.
+ * The reference has no FFI for this path (it is stock PyTorch); each entry
+ * point below names the reference code it replaces.  The host-side mirror of
+ * the reference's plugin interface (realpdebench.model.fno / load_model /
+ * eval.py rollout) lives in realpdebench_b200/ and binds these symbols with
+ * ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every data pointer is CALLER-OWNED DEVICE memory (fp32 unless stated);
+ *     the library owns only the small constant tables inside the plan;
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*); no hidden synchronisation, no allocation after plan creation:
+ *     every entry point that takes a stream is CUDA-graph capturable;
+ *   - functions return 0 on success or a negative B200FNO_E* code; the message
+ *     is available from b200fno_last_error() (thread-local).  No C++ exception
+ *     crosses the ABI;
+ *   - a plan is not thread-safe: one plan per (device, stream).
+ */
+#ifndef B200FNO_H
+#define B200FNO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FNO_ABI_VERSION 1
+
+#define B200FNO_OK 0
+#define B200FNO_EINVAL (-1)   /* bad descriptor / argument */
+#define B200FNO_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define B200FNO_ENODEV (-3)   /* no CUDA device / not an sm_100 part */
+#define B200FNO_ESTATE (-4)   /* weights not packed, workspace not bound, ... */
+
+/* impl selector for b200fno_plan_set_impl */
+#define B200FNO_IMPL_AUTO 0   /* tensor-core path where the shape allows, else SIMT */
+#define B200FNO_IMPL_SIMT 1   /* fp32 FFMA kernels (every shape) */
+#define B200FNO_IMPL_TC 2     /* tcgen05 3xTF32 kernels (width 64/128 only); error otherwise */
+
+typedef struct b200fno_plan b200fno_plan_t;
+
+/*
+ * Model + problem description.  Mirrors the constructor arguments of
+ * FNO3d(modes1, modes2, modes3, n_layers, width, shape_in, shape_out)
+ * (reference realpdebench/model/fno.py:67-103, called from
+ * model/load_model.py:12-22) plus the batch size the workspace is sized for.
+ *
+ * ndim = 3: FNO3d as shipped; FFT axes (T,H,W), lift features c_in + 3 grid
+ *           coordinates, projection features c_out * (t_out / t_in).
+ * ndim = 2: FNO-2D of SURVEY.md 8(c): frames folded into channels; FFT axes
+ *           (H,W); lift features t_in*c_in + 2; projection t_out*c_out;
+ *           modes1 is ignored (YAML modes2,modes3 -> 2-D modes).
+ */
+typedef struct b200fno_desc {
+  int32_t abi_version; /* B200FNO_ABI_VERSION */
+  int32_t ndim;        /* 2 | 3 */
+  int32_t max_batch;   /* workspace is sized for this many samples */
+  int32_t t_in, t_out; /* frames in / out (shape_in[0], shape_out[0]) */
+  int32_t h, w;        /* spatial grid (shape_in[1], shape_in[2]) */
+  int32_t c_in, c_out; /* physical channels (shape_in[3], shape_out[3]) */
+  int32_t width;       /* hidden channels */
+  int32_t n_layers;
+  int32_t modes1, modes2, modes3;
+  int32_t padding;     /* fno.py:87 -> 6 */
+  int32_t proj_hidden; /* fno.py:102 -> 128 */
+  float bn_eps;        /* nn.BatchNorm3d default 1e-5 */
+} b200fno_desc_t;
+
+/*
+ * Device pointers to the parameters in the REFERENCE state_dict layout
+ * (checkpoint row).  Arrays are host arrays of device
+ * pointers with one entry per layer (spec_w: n_layers * ncorner, corner-major
+ * inside a layer: weights1..4, fno.py:31-38; ncorner = 4 for ndim 3, 2 for 2).
+ * Spectral weights are complex64 [Ci][Co][m1][m2][m3] = interleaved (re,im) floats.
+ */
+typedef struct b200fno_weights {
+  const float* fc0_w;             /* [width][lift_features]  nn.Linear weight, fno.py:89 */
+  const float* fc0_b;             /* [width] */
+  const float* const* spec_w;     /* complex64, see above */
+  const float* const* conv_w;     /* [width][width] (1x1x1 kernel squeezed), fno.py:99 */
+  const float* const* conv_b;     /* [width] */
+  const float* const* bn_weight;  /* [width] fno.py:100 */
+  const float* const* bn_bias;
+  const float* const* bn_mean;    /* running_mean */
+  const float* const* bn_var;     /* running_var */
+  const float* fc1_w;             /* [proj_hidden][width] fno.py:102 */
+  const float* fc1_b;
+  const float* fc2_w;             /* [proj_features][proj_hidden] fno.py:103 */
+  const float* fc2_b;
+} b200fno_weights_t;
+
+/* Thread-local message of the last failing call on this thread. */
+const char* b200fno_last_error(void);
+int b200fno_abi_version(void);
+
+/* ---- plan life cycle ---------------------------------------------------- */
+/* Replaces FNO3d.__init__'s shape bookkeeping (fno.py:78-87): validates the
+ * descriptor, builds the truncated-DFT tables on the current device. */
+int b200fno_plan_create(const b200fno_desc_t* desc, b200fno_plan_t** out);
+int b200fno_plan_destroy(b200fno_plan_t* plan);
+int b200fno_plan_set_impl(b200fno_plan_t* plan, int impl);
+/* Which implementation the layer kernels resolve to (B200FNO_IMPL_SIMT|TC). */
+int b200fno_plan_get_impl(const b200fno_plan_t* plan);
+
+/* Bytes the caller must provide (activation ping-pong + spectral scratch). */
+size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* plan);
+/* Bytes of the packed (engine-layout) copy of the parameters. */
+size_t b200fno_plan_packed_bytes(const b200fno_plan_t* plan);
+int b200fno_plan_bind(b200fno_plan_t* plan, void* workspace, size_t workspace_bytes,
+                      void* packed, size_t packed_bytes);
+
+/* Re-pack parameters from the reference layout into `packed` (device kernels
+ * on `stream`): transposes, zero-pads channels to a multiple of 4, folds
+ * conv bias + eval-mode BatchNorm (fno.py:115-117) into one per-channel
+ * affine, resolves overlapping spectral corners the way the successive
+ * assignments fno.py:53-60 do (later corner wins). */
+int b200fno_pack_weights(b200fno_plan_t* plan, const b200fno_weights_t* w, void* stream);
+
+/* ---- the hot path ------------------------------------------------------- */
+/* FNO3d.forward (fno.py:105-129), eval-mode BatchNorm.
+ *   x [batch][t_in][h][w][c_in]  ->  y [batch][t_out][h][w][c_out]  */
+int b200fno_forward(b200fno_plan_t* plan, int32_t batch, const float* x, float* y, void* stream);
+
+/* The autoregressive loop eval.py:313-321 for one batch, with the
+ * de-normalise / concat-parameters / re-normalise glue (eval.py:315-318,
+ * data_normalizer.py:50-62) folded into the projection epilogue as the
+ * per-channel affine  p' = p * affine_a[c] + affine_b[c]  (SURVEY F6).
+ *   x0    [batch][t_in][h][w][c_in]   normalised input (output of preprocess)
+ *   pred  [batch][n_steps*t_out][h][w][c_out]  = torch.cat(preds[1:],1)[..., :c_out]
+ *   state [2][batch][t_in][h][w][c_in] scratch for the fed-back inputs
+ *         (may be NULL when n_steps == 1); parameter channels c_out..c_in-1
+ *         are carried over from x0 (eval.py:317).
+ * n_steps > 1 requires t_out == t_in. */
+int b200fno_rollout(b200fno_plan_t* plan, int32_t batch, const float* x0, const float* affine_a,
+                    const float* affine_b, int32_t n_steps, float* state, float* pred, void* stream);
+
+/* SpectralConv3d.forward (fno.py:45-64) / its 2-D analogue as a stand-alone
+ * operator in the REFERENCE tensor layout (channels first):
+ *   x [batch][ci][t][h][w] -> y [batch][co][t][h][w]       (ndim 3)
+ *   x [batch][ci][h][w]    -> y [batch][co][h][w]          (ndim 2)
+ * weights: ncorner device pointers, complex64 [ci][co][m1][m2][m3].
+ * workspace: b200fno_spectral_workspace_bytes(...) bytes of device scratch. */
+size_t b200fno_spectral_workspace_bytes(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t,
+                                        int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3);
+int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t, int32_t h,
+                          int32_t w, int32_t m1, int32_t m2, int32_t m3, const float* const* weights,
+                          const float* x, float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection used by bench.py / tests ------------------------------ */
+/* Kernels launched by this library on this thread since the last reset. */
+int64_t b200fno_launch_count(void);
+void b200fno_launch_count_reset(void);
+/* Host copy of truncated-DFT table `which` (0 fwdW, 1 fwdH, 2 fwdT, 3 invT, 4 invH,
+ * 5 invW) for a transformed grid (t,h,w) -- the values the kernels multiply by.
+ * Needs no device.  Writes at most `cap` floats to `out`, the row pitch to *ld and
+ * the kept T / H frequency indices to freqs_t / freqs_h (each sized >= t / h;
+ * may be NULL).  Returns the table length in floats or a negative error code. */
+int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
+                           int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t, int32_t* freqs_h);
+/* Algorithmic HBM bytes of one forward at `batch` (SURVEY.md 8d formula). */
+double b200fno_algorithmic_bytes(const b200fno_plan_t* plan, int32_t batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FNO_H */

@@ -1,0 +1,22 @@
+"""B200-native FNO forward / rollout engine behind RealPDEBench's model registry.
+
+Public surface (mirrors the reference names):
+
+* ``FNO3d`` / ``SpectralConv3d``  - realpdebench/model/fno.py
+* ``FNO2d`` / ``SpectralConv2d``  - the 2-D variant defined in SURVEY.md 8(c)
+* ``load_model``                  - realpdebench/model/load_model.py (+ ``fno2d``)
+* ``rollout``                     - realpdebench/eval.py:296-326 for one batch
+* ``install``                     - registers the above at ``realpdebench.model.fno``
+                                    so the unmodified reference scripts use them
+
+The arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of
+``include/b200fno.h``; there is no CPU or PyTorch fallback.
+"""
+from .fno import FNO2d, FNO3d, SpectralConv2d, SpectralConv3d
+from .install import install, uninstall
+from .load_model import load_model
+from .rollout import rollout, rollout_affine
+
+__all__ = ["FNO3d", "FNO2d", "SpectralConv3d", "SpectralConv2d", "load_model", "rollout", "rollout_affine",
+           "install", "uninstall"]
+__version__ = "0.1.0"

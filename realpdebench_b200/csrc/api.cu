@@ -1,0 +1,548 @@
+// Plan object and the extern "C" entry points declared in include/b200fno.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+namespace b200fno {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int64_t& launch_counter() { return g_launches; }
+
+}  // namespace b200fno
+
+using namespace b200fno;
+
+struct LayerPacked {
+  float *convT, *scale, *shift, *spec;
+};
+
+struct b200fno_plan {
+  b200fno_desc_t d;
+  Geom g;
+  Tables tab;
+  int device = 0;
+  int impl_request = B200FNO_IMPL_AUTO;
+  // derived feature bookkeeping
+  int Fin, ng, Klp, Fout, Fp, Tv;  // Tv: valid t rows of the activation grid (t_in for 3-D, 1 for 2-D)
+  int ncorner;
+  // device tables owned by the plan
+  float* d_grid = nullptr;  // gt | gh | gw
+  int* d_int = nullptr;     // in_off | chan | out_off | st_off
+  const float *gt = nullptr, *gh = nullptr, *gw = nullptr;
+  const int *in_off = nullptr, *chan = nullptr, *out_off = nullptr, *st_off = nullptr;
+  // caller-owned
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* packed = nullptr;
+  size_t packed_bytes = 0;
+  bool weights_ready = false;
+  // views into ws / packed
+  float *act[2], *bufAD, *bufBC, *bufS, *bufO;
+  float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
+  std::vector<LayerPacked> layers;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int make_geom(int ndim, int T, int H, int W, int C, int m1, int m2, int m3, Geom* g) {
+  g->ndim = ndim;
+  g->Tp = ndim == 3 ? T : 1;
+  g->Hp = H;
+  g->Wp = W;
+  g->Cp = round_up(C, 4);
+  g->m3 = m3;
+  if (m2 < 1 || m3 < 1 || m2 > H || m3 > W / 2 + 1 || (ndim == 3 && (m1 < 1 || m1 > T))) {
+    set_error("modes (%d,%d,%d) do not fit the transformed grid (%d,%d,%d): need m1<=T', m2<=H', m3<=W'/2+1", m1, m2,
+              m3, g->Tp, H, W);
+    return B200FNO_EINVAL;
+  }
+  g->KH = std::min(2 * m2, H);
+  g->KT = ndim == 3 ? std::min(2 * m1, T) : 1;
+  g->K2 = 2 * m3;
+  g->K2p = round_up(g->K2, 4);
+  g->NM = g->KT * g->KH * m3;
+  return 0;
+}
+
+static size_t spectral_scratch_floats(const Geom& g, int B) {
+  return align_up(g.a_elems(B), 64) + align_up(g.b_elems(B), 64) + 2 * align_up(g.s_elems(B), 64);
+}
+
+// The truncated-DFT spectral operator on a channels-last activation:
+//   act -> D   (everything of SpectralConv3d.forward except the last inverse-W stage,
+//               which the layer kernel fuses with the bypass conv)
+static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
+                        float* bufBC, float* bufS, float* bufO, cudaStream_t st) {
+  const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
+  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
+  B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD, (long long)g.K2 * g.Cp,
+                     g.Cp, g.Cp, B * g.Tp * g.Hp, st));
+  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
+  float* fwdH_out = g.ndim == 3 ? bufBC : bufS;
+  B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
+                     2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  if (g.ndim == 3) {
+    const long long n_t = (long long)g.KH * n_hw;
+    B2_TRY(launch_lmul(tab.LT, tab.ldLT, 2 * g.KT, 2 * g.Tp, bufBC, (long long)g.Tp * 2 * n_t, n_t, bufS,
+                       2LL * g.KT * n_t, n_t, (int)n_t, B, st));
+  }
+  B2_TRY(launch_modes(bufS, Wpk, bufO, B, g.NM, g.Cp, st));
+  const float* invH_in = bufO;
+  if (g.ndim == 3) {
+    const long long n_t = (long long)g.KH * n_hw;
+    B2_TRY(launch_lmul(tab.LTi, tab.ldLTi, 2 * g.Tp, 2 * g.KT, bufO, 2LL * g.KT * n_t, n_t, bufBC,
+                       (long long)g.Tp * 2 * n_t, n_t, (int)n_t, B, st));
+    invH_in = bufBC;
+  }
+  B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
+                     (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  return 0;
+}
+
+static int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return B200FNO_ENODEV;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess || p.major != 10) {
+    set_error("b200fno is built for sm_100a only; device %d is sm_%d%d", dev, p.major, p.minor);
+    return B200FNO_ENODEV;
+  }
+  return 0;
+}
+
+extern "C" {
+
+const char* b200fno_last_error(void) { return g_err; }
+int b200fno_abi_version(void) { return B200FNO_ABI_VERSION; }
+int64_t b200fno_launch_count(void) { return g_launches; }
+void b200fno_launch_count_reset(void) { g_launches = 0; }
+
+int b200fno_plan_create(const b200fno_desc_t* d, b200fno_plan_t** out) {
+  if (!d || !out) {
+    set_error("null argument");
+    return B200FNO_EINVAL;
+  }
+  *out = nullptr;
+  if (d->abi_version != B200FNO_ABI_VERSION) {
+    set_error("descriptor abi_version %d != library %d", d->abi_version, B200FNO_ABI_VERSION);
+    return B200FNO_EINVAL;
+  }
+  if ((d->ndim != 2 && d->ndim != 3) || d->max_batch < 1 || d->t_in < 1 || d->t_out < 1 || d->h < 1 || d->w < 1 ||
+      d->c_in < 1 || d->c_out < 1 || d->width < 1 || d->n_layers < 1 || d->padding < 0) {
+    set_error("bad descriptor field (ndim must be 2|3, sizes >= 1)");
+    return B200FNO_EINVAL;
+  }
+  if (d->proj_hidden != 128) {
+    set_error("proj_hidden must be 128 (fno.py:102), got %d", d->proj_hidden);
+    return B200FNO_EINVAL;
+  }
+  if (d->ndim == 3 && d->t_out % d->t_in != 0) {
+    set_error("t_out (%d) must be a multiple of t_in (%d) (fno.py:86)", d->t_out, d->t_in);
+    return B200FNO_EINVAL;
+  }
+  B2_TRY(check_device());
+  b200fno_plan* p = new (std::nothrow) b200fno_plan();
+  if (!p) {
+    set_error("out of host memory");
+    return B200FNO_EINVAL;
+  }
+  p->d = *d;
+  cudaGetDevice(&p->device);
+  const int pad = d->padding;
+  int rc = make_geom(d->ndim, d->t_in + pad, d->h + pad, d->w + pad, d->width, d->modes1, d->modes2, d->modes3, &p->g);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  rc = build_tables(p->g, d->modes1, d->modes2, &p->tab);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  const int T = d->t_in, H = d->h, W = d->w, Ci = d->c_in, Co = d->c_out;
+  if (d->ndim == 3) {
+    p->Fin = Ci, p->ng = 3, p->Fout = Co * (d->t_out / T), p->Tv = T, p->ncorner = 4;
+  } else {
+    p->Fin = T * Ci, p->ng = 2, p->Fout = d->t_out * Co, p->Tv = 1, p->ncorner = 2;
+  }
+  p->Klp = round_up(p->Fin + p->ng + 1, 4);
+  p->Fp = round_up(p->Fout, 4);
+  // grid coordinates: fp32(np.linspace(0,1,n)) (fno.py:137-141)
+  std::vector<float> grid(T + H + W);
+  auto lin = [](float* o, int n) {
+    for (int i = 0; i < n; ++i) o[i] = (n == 1) ? 0.f : (i == n - 1 ? 1.f : (float)((double)i * (1.0 / (double)(n - 1))));
+  };
+  lin(grid.data(), T), lin(grid.data() + T, H), lin(grid.data() + T + H, W);
+  std::vector<int> ints(p->Fin + 3 * p->Fout);
+  int* in_off = ints.data();
+  int *chan = in_off + p->Fin, *out_off = chan + p->Fout, *st_off = out_off + p->Fout;
+  const long long HW = (long long)H * W;
+  if (d->ndim == 3) {
+    const int r = d->t_out / T;
+    for (int j = 0; j < p->Fin; ++j) in_off[j] = j;
+    for (int f = 0; f < p->Fout; ++f) {  // fno.py:127-128: feature f = c*r + rho -> frame t*r + rho, channel c
+      int c = f / r, rho = f % r;
+      chan[f] = c;
+      out_off[f] = (int)(rho * HW * Co + c);
+      st_off[f] = (int)(rho * HW * Ci + c);
+    }
+  } else {
+    for (int j = 0; j < p->Fin; ++j) in_off[j] = (int)((j / Ci) * HW * Ci + (j % Ci));
+    for (int f = 0; f < p->Fout; ++f) {
+      int to = f / Co, c = f % Co;
+      chan[f] = c;
+      out_off[f] = (int)(to * HW * Co + c);
+      st_off[f] = (int)(to * HW * Ci + c);
+    }
+  }
+  auto fail = [&](const char* what, cudaError_t e) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    b200fno_plan_destroy(p);
+    return B200FNO_ECUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc((void**)&p->d_grid, grid.size() * sizeof(float))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc((void**)&p->d_int, ints.size() * sizeof(int))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMemcpy(p->d_grid, grid.data(), grid.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail("cudaMemcpy", e);
+  if ((e = cudaMemcpy(p->d_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail("cudaMemcpy", e);
+  p->gt = d->ndim == 3 ? p->d_grid : nullptr;
+  p->gh = p->d_grid + T;
+  p->gw = p->d_grid + T + H;
+  p->in_off = p->d_int;
+  p->chan = p->d_int + p->Fin;
+  p->out_off = p->chan + p->Fout;
+  p->st_off = p->out_off + p->Fout;
+  *out = p;
+  return 0;
+}
+
+int b200fno_plan_destroy(b200fno_plan_t* p) {
+  if (!p) return 0;
+  free_tables(&p->tab);
+  if (p->d_grid) cudaFree(p->d_grid);
+  if (p->d_int) cudaFree(p->d_int);
+  delete p;
+  return 0;
+}
+
+int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
+  if (!p || impl < B200FNO_IMPL_AUTO || impl > B200FNO_IMPL_TC) {
+    set_error("bad impl selector");
+    return B200FNO_EINVAL;
+  }
+  if (impl == B200FNO_IMPL_TC) {
+    set_error("tensor-core layer kernels are not available for this shape (width %d)", p->d.width);
+    return B200FNO_EINVAL;
+  }
+  p->impl_request = impl;
+  return 0;
+}
+int b200fno_plan_get_impl(const b200fno_plan_t* p) { return p ? B200FNO_IMPL_SIMT : B200FNO_EINVAL; }
+
+size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* p) {
+  if (!p) return 0;
+  const int B = p->d.max_batch;
+  return (2 * align_up(p->g.act_elems(B), 64) + spectral_scratch_floats(p->g, B)) * sizeof(float);
+}
+
+static size_t packed_floats(const b200fno_plan* p) {
+  const Geom& g = p->g;
+  size_t n = align_up((size_t)p->Klp * g.Cp, 64);
+  n += (size_t)p->d.n_layers *
+       (align_up((size_t)g.Cp * g.Cp, 64) + 2 * align_up(g.Cp, 64) + align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64));
+  n += align_up((size_t)g.Cp * 128, 64) + 128 + align_up((size_t)128 * p->Fp, 64) + align_up(p->Fp, 64);
+  return n;
+}
+size_t b200fno_plan_packed_bytes(const b200fno_plan_t* p) { return p ? packed_floats(p) * sizeof(float) : 0; }
+
+int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes, void* packed, size_t packed_bytes) {
+  if (!p || !workspace || !packed) {
+    set_error("null argument");
+    return B200FNO_EINVAL;
+  }
+  if (workspace_bytes < b200fno_plan_workspace_bytes(p) || packed_bytes < b200fno_plan_packed_bytes(p)) {
+    set_error("buffers too small: workspace %zu < %zu or packed %zu < %zu", workspace_bytes,
+              b200fno_plan_workspace_bytes(p), packed_bytes, b200fno_plan_packed_bytes(p));
+    return B200FNO_EINVAL;
+  }
+  if (((uintptr_t)workspace | (uintptr_t)packed) & 255) {
+    set_error("workspace and packed buffers must be 256-byte aligned");
+    return B200FNO_EINVAL;
+  }
+  const Geom& g = p->g;
+  const int B = p->d.max_batch;
+  float* w = (float*)workspace;
+  p->ws = w, p->ws_bytes = workspace_bytes;
+  p->act[0] = w, w += align_up(g.act_elems(B), 64);
+  p->act[1] = w, w += align_up(g.act_elems(B), 64);
+  p->bufAD = w, w += align_up(g.a_elems(B), 64);
+  p->bufBC = w, w += align_up(g.b_elems(B), 64);
+  p->bufS = w, w += align_up(g.s_elems(B), 64);
+  p->bufO = w;
+  float* q = (float*)packed;
+  p->packed = q, p->packed_bytes = packed_bytes;
+  p->W0T = q, q += align_up((size_t)p->Klp * g.Cp, 64);
+  p->layers.resize(p->d.n_layers);
+  for (auto& L : p->layers) {
+    L.convT = q, q += align_up((size_t)g.Cp * g.Cp, 64);
+    L.scale = q, q += align_up(g.Cp, 64);
+    L.shift = q, q += align_up(g.Cp, 64);
+    L.spec = q, q += align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64);
+  }
+  p->fc1T = q, q += align_up((size_t)g.Cp * 128, 64);
+  p->fc1b = q, q += 128;
+  p->fc2T = q, q += align_up((size_t)128 * p->Fp, 64);
+  p->fc2b = q;
+  p->weights_ready = false;
+  return 0;
+}
+
+int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* stream) {
+  if (!p || !w) {
+    set_error("null argument");
+    return B200FNO_EINVAL;
+  }
+  if (!p->packed) {
+    set_error("b200fno_plan_bind must be called before b200fno_pack_weights");
+    return B200FNO_ESTATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geom& g = p->g;
+  const int C = p->d.width, nf = p->Fin + p->ng;
+  B2_TRY(launch_transpose_pad(w->fc0_w, C, nf, p->W0T, p->Klp, g.Cp, st));
+  B2_TRY(launch_pad_copy(w->fc0_b, C, p->W0T + (size_t)nf * g.Cp, g.Cp, st));
+  for (int l = 0; l < p->d.n_layers; ++l) {
+    LayerPacked& L = p->layers[l];
+    B2_TRY(launch_transpose_pad(w->conv_w[l], C, C, L.convT, g.Cp, g.Cp, st));
+    B2_TRY(launch_fold_bn(w->conv_b[l], w->bn_weight[l], w->bn_bias[l], w->bn_mean[l], w->bn_var[l], p->d.bn_eps, C,
+                          g.Cp, L.scale, L.shift, st));
+    B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, L.spec, g, C, C, p->d.modes1,
+                                p->d.modes2, p->tab.d_ft, p->tab.d_fh, st));
+  }
+  B2_TRY(launch_transpose_pad(w->fc1_w, 128, C, p->fc1T, g.Cp, 128, st));
+  B2_TRY(launch_pad_copy(w->fc1_b, 128, p->fc1b, 128, st));
+  B2_TRY(launch_transpose_pad(w->fc2_w, p->Fout, 128, p->fc2T, 128, p->Fp, st));
+  B2_TRY(launch_pad_copy(w->fc2_b, p->Fout, p->fc2b, p->Fp, st));
+  p->weights_ready = true;
+  return 0;
+}
+
+// lift + L Fourier layers; leaves the last layer's output in *final_act
+static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final_act, cudaStream_t st) {
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  LiftArgs la{};
+  la.x = x, la.act = p->act[0], la.W0T = p->W0T, la.in_off = p->in_off;
+  la.gt = p->gt, la.gh = p->gh, la.gw = p->gw;
+  la.B = B, la.T = p->Tv, la.H = d.h, la.W = d.w, la.Tp = g.Tp, la.Hp = g.Hp, la.Wp = g.Wp, la.Cp = g.Cp;
+  la.c_in = d.c_in, la.Fin = p->Fin, la.ng = p->ng, la.Klp = p->Klp;
+  la.x_sB = (long long)d.t_in * d.h * d.w * d.c_in;
+  la.x_sT = d.ndim == 3 ? (long long)d.h * d.w * d.c_in : 0;
+  B2_TRY(launch_lift(la, st));
+  int cur = 0;
+  const long long rows = (long long)B * g.Tp * g.Hp;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const LayerPacked& L = p->layers[l];
+    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st));
+    B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows, g.Wp,
+                        g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
+    cur ^= 1;
+  }
+  *final_act = p->act[cur];
+  return 0;
+}
+
+static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a, const float* aff_b, float* out,
+                    long long out_sB, float* state, cudaStream_t st) {
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  ProjArgs pa{};
+  pa.act = act, pa.fc1T = p->fc1T, pa.fc1b = p->fc1b, pa.fc2T = p->fc2T, pa.fc2b = p->fc2b;
+  pa.aff_a = aff_a, pa.aff_b = aff_b, pa.chan = p->chan, pa.out_off = p->out_off, pa.st_off = p->st_off;
+  pa.out = out, pa.state = state;
+  pa.B = B, pa.T = p->Tv, pa.H = d.h, pa.W = d.w, pa.Tp = g.Tp, pa.Hp = g.Hp, pa.Wp = g.Wp, pa.Cp = g.Cp;
+  pa.Fout = p->Fout, pa.Fp = p->Fp, pa.c_out = d.c_out, pa.c_in = d.c_in;
+  const long long HW = (long long)d.h * d.w;
+  pa.out_sB = out_sB;
+  pa.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
+  pa.st_sB = (long long)d.t_in * HW * d.c_in;
+  pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
+  return launch_proj(pa, st);
+}
+
+static int check_ready(b200fno_plan* p, int batch) {
+  if (!p) {
+    set_error("null plan");
+    return B200FNO_EINVAL;
+  }
+  if (!p->ws || !p->weights_ready) {
+    set_error("plan not ready: bind buffers and pack weights first");
+    return B200FNO_ESTATE;
+  }
+  if (batch < 1 || batch > p->d.max_batch) {
+    set_error("batch %d outside [1, max_batch=%d]", batch, p->d.max_batch);
+    return B200FNO_EINVAL;
+  }
+  return 0;
+}
+
+int b200fno_forward(b200fno_plan_t* p, int32_t batch, const float* x, float* y, void* stream) {
+  B2_TRY(check_ready(p, batch));
+  if (!x || !y) {
+    set_error("null tensor");
+    return B200FNO_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* fin = nullptr;
+  B2_TRY(run_trunk(p, batch, x, &fin, st));
+  const long long out_sB = (long long)p->d.t_out * p->d.h * p->d.w * p->d.c_out;
+  return run_proj(p, batch, fin, nullptr, nullptr, y, out_sB, nullptr, st);
+}
+
+int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const float* affine_a, const float* affine_b,
+                    int32_t n_steps, float* state, float* pred, void* stream) {
+  B2_TRY(check_ready(p, batch));
+  const b200fno_desc_t& d = p->d;
+  if (!x0 || !pred || !affine_a || !affine_b || n_steps < 1) {
+    set_error("null tensor or n_steps < 1");
+    return B200FNO_EINVAL;
+  }
+  if (n_steps > 1 && (d.t_out != d.t_in || !state)) {
+    set_error("n_steps > 1 needs t_out == t_in (got %d, %d) and a state buffer", d.t_out, d.t_in);
+    return B200FNO_EINVAL;
+  }
+  if (d.c_in < d.c_out) {
+    set_error("c_in (%d) < c_out (%d): prediction cannot be fed back", d.c_in, d.c_out);
+    return B200FNO_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long HW = (long long)d.h * d.w;
+  const long long state_elems = (long long)batch * d.t_in * HW * d.c_in;
+  const long long step_elems = (long long)d.t_out * HW * d.c_out;
+  const long long out_sB = (long long)n_steps * step_elems;
+  if (n_steps > 1 && d.c_in > d.c_out)
+    B2_TRY(launch_copy_params(x0, state, (long long)batch * d.t_in * HW, d.c_in, d.c_out, st));
+  const float* cur = x0;
+  for (int i = 0; i < n_steps; ++i) {
+    const float* fin = nullptr;
+    B2_TRY(run_trunk(p, batch, cur, &fin, st));
+    float* next = (i + 1 < n_steps) ? state + (size_t)(i & 1) * state_elems : nullptr;
+    B2_TRY(run_proj(p, batch, fin, affine_a, affine_b, pred + (size_t)i * step_elems, out_sB, next, st));
+    cur = next;
+  }
+  return 0;
+}
+
+size_t b200fno_spectral_workspace_bytes(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t, int32_t h,
+                                        int32_t w, int32_t m1, int32_t m2, int32_t m3) {
+  Geom g;
+  if (make_geom(ndim, t, h, w, std::max(ci, co), m1, m2, m3, &g)) return 0;
+  size_t n = 2 * align_up(g.act_elems(batch), 64) + spectral_scratch_floats(g, batch) +
+             align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64);
+  return n * sizeof(float);
+}
+
+int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t, int32_t h, int32_t w,
+                          int32_t m1, int32_t m2, int32_t m3, const float* const* weights, const float* x, float* y,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if ((ndim != 2 && ndim != 3) || batch < 1 || ci < 1 || co < 1 || !weights || !x || !y || !workspace) {
+    set_error("bad argument");
+    return B200FNO_EINVAL;
+  }
+  B2_TRY(check_device());
+  Geom g;
+  B2_TRY(make_geom(ndim, t, h, w, std::max(ci, co), m1, m2, m3, &g));
+  const size_t need = b200fno_spectral_workspace_bytes(ndim, batch, ci, co, t, h, w, m1, m2, m3);
+  if (workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+    set_error("spectral workspace too small (%zu < %zu) or not 256-byte aligned", workspace_bytes, need);
+    return B200FNO_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // Tables are rebuilt per call: this entry point is the stand-alone operator used for
+  // layer-level parity and by callers outside FNO3d; the model path keeps them in the plan.
+  Tables tab;
+  B2_TRY(build_tables(g, m1, m2, &tab));
+  float* ws = (float*)workspace;
+  float* a0 = ws;
+  ws += align_up(g.act_elems(batch), 64);
+  float* a1 = ws;
+  ws += align_up(g.act_elems(batch), 64);
+  float* bufAD = ws;
+  ws += align_up(g.a_elems(batch), 64);
+  float* bufBC = ws;
+  ws += align_up(g.b_elems(batch), 64);
+  float* bufS = ws;
+  ws += align_up(g.s_elems(batch), 64);
+  float* bufO = ws;
+  ws += align_up(g.s_elems(batch), 64);
+  float* Wpk = ws;
+  const long long S = (long long)g.Tp * g.Hp * g.Wp;
+  int rc = launch_pack_spectral(weights, ndim == 3 ? 4 : 2, Wpk, g, ci, co, m1, m2, tab.d_ft, tab.d_fh, st);
+  if (!rc) rc = launch_nchw_to_cl(x, a0, batch, ci, S, g.Cp, st);
+  if (!rc) rc = run_spectral(g, tab, batch, a0, Wpk, bufAD, bufBC, bufS, bufO, st);
+  if (!rc)
+    rc = launch_layer(a0, a1, nullptr, tab.Gt, bufAD, nullptr, nullptr, (long long)batch * g.Tp * g.Hp, g.Wp, g.Cp,
+                      g.K2, g.K2p, 0, st);
+  if (!rc) rc = launch_cl_to_nchw(a1, y, batch, co, S, g.Cp, st);
+  // the tables must outlive the kernels that read them
+  cudaError_t e = cudaStreamSynchronize(st);
+  free_tables(&tab);
+  if (!rc && e != cudaSuccess) {
+    set_error("spectral_conv: %s", cudaGetErrorString(e));
+    rc = B200FNO_ECUDA;
+  }
+  return rc;
+}
+
+int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
+                           int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t, int32_t* freqs_h) {
+  if ((ndim != 2 && ndim != 3) || which < 0 || which > 5) {
+    set_error("bad argument");
+    return B200FNO_EINVAL;
+  }
+  Geom g;
+  B2_TRY(make_geom(ndim, t, h, w, 4, m1, m2, m3, &g));
+  Tables tab;
+  std::vector<float> host[6];
+  B2_TRY(compute_tables_host(g, m1, m2, &tab, host));
+  const int lds[6] = {tab.ldLF, tab.ldLH, tab.ldLT, tab.ldLTi, tab.ldLHi, g.K2p};
+  if (ld) *ld = lds[which];
+  if (freqs_t) std::copy(tab.ft.begin(), tab.ft.end(), freqs_t);
+  if (freqs_h) std::copy(tab.fh.begin(), tab.fh.end(), freqs_h);
+  const int64_t n = (int64_t)host[which].size();
+  if (out) std::copy(host[which].begin(), host[which].begin() + std::min(n, cap), out);
+  return n;
+}
+
+double b200fno_algorithmic_bytes(const b200fno_plan_t* p, int32_t batch) {
+  if (!p) return 0.0;
+  const b200fno_desc_t& d = p->d;
+  const Geom& g = p->g;
+  // B*[in + out + L*2*C*T'H'W'*4] + L*C^2*K*8, K = corner modes as configured
+  const double pts = (double)d.h * d.w;
+  const double in = (double)d.t_in * pts * d.c_in * 4, out = (double)d.t_out * pts * d.c_out * 4;
+  const double act = (double)d.width * g.Tp * g.Hp * g.Wp * 4;
+  const double K = (d.ndim == 3 ? 4.0 * d.modes1 : 2.0) * d.modes2 * d.modes3;
+  return batch * (in + out + d.n_layers * 2.0 * act) + (double)d.n_layers * d.width * d.width * K * 8.0;
+}
+
+}  // extern "C"

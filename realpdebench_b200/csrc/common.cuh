@@ -1,0 +1,133 @@
+// Shared declarations for the b200fno engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fno.h"
+
+namespace b200fno {
+
+// ---- error plumbing ----------------------------------------------------------
+void set_error(const char* fmt, ...);
+int64_t& launch_counter();
+
+#define B2_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      b200fno::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                         \
+      return B200FNO_ECUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+#define B2_LAUNCHED(name)                                                                     \
+  do {                                                                                        \
+    ++b200fno::launch_counter();                                                              \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      b200fno::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e),    \
+                         __FILE__, __LINE__);                                                 \
+      return B200FNO_ECUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+#define B2_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
+
+// ---- geometry of the truncated-DFT pipeline ----------------------------------
+// Activations are channels-last fp32 [B][Tp][Hp][Wp][Cp] (Tp == 1 for ndim 2).
+// Spectral intermediates (ri = 0 real, 1 imaginary; n = contiguous tail):
+//   A  = fwdW(act)   [B][Tp][Hp][ri][m3][Cp]
+//   Bh = fwdH(A)     [B][Tp][ri][KH][m3][Cp]
+//   S  = fwdT(Bh)    [B][ri][KT][KH][m3][Cp]     (ndim 2: S == Bh, KT == 1)
+//   O  = modes(S)    [B][ri][KT][KH][m3][Cp]
+//   Ct = invT(O)     [B][Tp][ri][KH][m3][Cp]
+//   D  = invH(Ct)    [B][Tp][Hp][ri][m3][Cp]
+//   act' = act(bn(conv(act) + invW(D)))
+struct Geom {
+  int ndim;
+  int Tp, Hp, Wp;  // padded (FFT) extents
+  int Cp;          // channels rounded up to a multiple of 4
+  int m3;          // kept W modes
+  int KT, KH;      // distinct kept T / H frequencies (<= 2*m1, 2*m2)
+  int K2;          // 2*m3 (re/im rows of the W transform)
+  int K2p;         // K2 rounded up to 4
+  int NM;          // KT*KH*m3 modes
+  size_t act_elems(int B) const { return (size_t)B * Tp * Hp * Wp * Cp; }
+  size_t a_elems(int B) const { return (size_t)B * Tp * Hp * K2 * Cp; }
+  size_t b_elems(int B) const { return (size_t)B * Tp * 2 * KH * m3 * Cp; }
+  size_t s_elems(int B) const { return (size_t)B * 2 * NM * Cp; }
+};
+
+// Constant tables (device, fp32) for one geometry; see tables.cu for the values.
+struct Tables {
+  float* base = nullptr;  // one cudaMalloc
+  size_t bytes = 0;
+  const float *LF = nullptr, *LH = nullptr, *LT = nullptr, *LTi = nullptr, *LHi = nullptr, *Gt = nullptr;
+  int ldLF = 0, ldLH = 0, ldLT = 0, ldLTi = 0, ldLHi = 0;
+  std::vector<int> ft, fh;  // actual frequency index of each kept T / H slot
+  int *d_ft = nullptr, *d_fh = nullptr;
+};
+int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6]);
+int build_tables(const Geom& g, int m1, int m2, Tables* t);
+void free_tables(Tables* t);
+
+// ---- SIMT stage launchers (simt.cu) ------------------------------------------
+// Out[g][m][n] = sum_k L[m][k] * R[g][k][n]   (n contiguous; N % 4 == 0)
+int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long strideRg, long long strideRk,
+                float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st);
+// O[b][ri][mode][o] = sum_i S[b][.][mode][i] (x) W[mode][i][.][o]   (complex)
+int launch_modes(const float* S, const float* Wpk, float* O, int B, int NM, int Cp, cudaStream_t st);
+// out[row][w][o] = f( (sum_i in[row][w][i] convT[i][o] + sum_k Gt[w][k] D[row][k][o]) * scale[o] + shift[o] )
+int launch_layer(const float* act_in, float* act_out, const float* convT, const float* Gt, const float* D,
+                 const float* scale, const float* shift, long long rows, int Wp, int Cp, int K2, int K2p, int gelu,
+                 cudaStream_t st);
+
+struct LiftArgs {
+  const float* x;       // [B][T][H][W][c_in]
+  float* act;           // [B][Tp][Hp][Wp][Cp]
+  const float* W0T;     // [Klp][Cp]  rows: features, grid coords, bias, zero pad
+  const int* in_off;    // [Fin]
+  const float *gt, *gh, *gw;  // grid coordinate tables (gt == nullptr for ndim 2)
+  int B, T, H, W, Tp, Hp, Wp, Cp, c_in, Fin, ng, Klp;
+  long long x_sB, x_sT;  // element strides of x for batch and (3-D) frame
+};
+int launch_lift(const LiftArgs& a, cudaStream_t st);
+
+struct ProjArgs {
+  const float* act;     // [B][Tp][Hp][Wp][Cp]
+  const float *fc1T, *fc1b, *fc2T, *fc2b;  // [Cp][128], [128], [128][Fp], [Fp]
+  const float *aff_a, *aff_b;              // per physical channel, may be nullptr (identity)
+  const int *chan, *out_off, *st_off;      // [Fout]
+  float* out;                              // prediction tensor (pre-offset to this step)
+  float* state;                            // next model input or nullptr
+  int B, T, H, W, Tp, Hp, Wp, Cp, Fout, Fp, c_out, c_in;
+  long long out_sB, out_sT, st_sB, st_sT;
+};
+int launch_proj(const ProjArgs& a, cudaStream_t st);
+
+// layout helpers for the stand-alone spectral operator
+int launch_nchw_to_cl(const float* x, float* act, int B, int C, long long S, int Cp, cudaStream_t st);
+int launch_cl_to_nchw(const float* act, float* y, int B, int C, long long S, int Cp, cudaStream_t st);
+int launch_copy_params(const float* x0, float* state, long long points, int c_in, int c_out, cudaStream_t st);
+
+// ---- weight packing (pack.cu) --------------------------------------------------
+int launch_pack_spectral(const float* const* corners_dev, int ncorner, float* Wpk, const Geom& g, int ci, int co,
+                         int m1, int m2, const int* d_ft, const int* d_fh, cudaStream_t st);
+int launch_transpose_pad(const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols,
+                         cudaStream_t st);  // dst[c][r] = src[r][c], zero elsewhere
+int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v,
+                   float eps, int C, int Cp, float* scale, float* shift, cudaStream_t st);
+int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st);
+
+}  // namespace b200fno

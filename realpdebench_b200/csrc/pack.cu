@@ -1,0 +1,115 @@
+// One-time re-layout of the reference parameters (state_dict layout, SURVEY
+// section 5) into the engine layout.  Runs on the caller's stream.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200fno {
+
+struct Corners {
+  const float* w[4];
+};
+
+// Wpk[mode][i][ri][o], mode = (kt_slot*KH + kh_slot)*m3 + kw.
+// Source corner tensors are complex64 [ci][co][m1][m2][m3] (3-D) / [ci][co][m2][m3] (2-D).
+// Which corner feeds a kept frequency follows the assignment order fno.py:53-60:
+// weights1 (low t, low h), weights2 (high t, low h), weights3 (low t, high h),
+// weights4 (high t, high h); where corners overlap the later assignment wins,
+// i.e. "high" beats "low" on each axis.
+__global__ void pack_spectral_kernel(Corners c, float* __restrict__ Wpk, int ndim, int Tp, int Hp, int m1, int m2,
+                                     int m3, int KT, int KH, int ci, int co, int Cp, const int* __restrict__ ft,
+                                     const int* __restrict__ fh) {
+  const size_t total = (size_t)KT * KH * m3 * Cp * 2 * Cp;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int o = (int)(idx % Cp);
+    size_t r = idx / Cp;
+    int ri = (int)(r & 1);
+    r >>= 1;
+    int i = (int)(r % Cp);
+    r /= Cp;
+    int kw = (int)(r % m3);
+    r /= m3;
+    int khs = (int)(r % KH);
+    int kts = (int)(r / KH);
+    float v = 0.f;
+    if (i < ci && o < co) {
+      const int fH = fh[khs];
+      const bool h_hi = fH >= Hp - m2;
+      const int y = h_hi ? fH - (Hp - m2) : fH;
+      if (ndim == 3) {
+        const int fT = ft[kts];
+        const bool t_hi = fT >= Tp - m1;
+        const int x = t_hi ? fT - (Tp - m1) : fT;
+        const float* src = c.w[(h_hi ? 2 : 0) + (t_hi ? 1 : 0)];
+        v = src[(((((size_t)i * co + o) * m1 + x) * m2 + y) * m3 + kw) * 2 + ri];
+      } else {
+        const float* src = c.w[h_hi ? 1 : 0];
+        v = src[((((size_t)i * co + o) * m2 + y) * m3 + kw) * 2 + ri];
+      }
+    }
+    Wpk[idx] = v;
+  }
+}
+
+int launch_pack_spectral(const float* const* corners, int ncorner, float* Wpk, const Geom& g, int ci, int co, int m1,
+                         int m2, const int* d_ft, const int* d_fh, cudaStream_t st) {
+  Corners c{};
+  for (int i = 0; i < ncorner; ++i) c.w[i] = corners[i];
+  size_t total = (size_t)g.NM * g.Cp * 2 * g.Cp;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  pack_spectral_kernel<<<blocks, 256, 0, st>>>(c, Wpk, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KT, g.KH, ci, co, g.Cp,
+                                               d_ft, d_fh);
+  B2_LAUNCHED("pack_spectral_kernel");
+  return 0;
+}
+
+// dst[c][r] = src[r][c] for r < rows, c < cols; zero elsewhere.  dst is [dst_rows][dst_cols].
+__global__ void transpose_pad_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst,
+                                     int dst_rows, int dst_cols) {
+  const int total = dst_rows * dst_cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int r = idx % dst_cols, c = idx / dst_cols;  // dst[c][r]
+    dst[idx] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+  }
+}
+int launch_transpose_pad(const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols,
+                         cudaStream_t st) {
+  int total = dst_rows * dst_cols;
+  transpose_pad_kernel<<<std::max(1, std::min((total + 255) / 256, 1024)), 256, 0, st>>>(src, rows, cols, dst,
+                                                                                          dst_rows, dst_cols);
+  B2_LAUNCHED("transpose_pad_kernel");
+  return 0;
+}
+
+// conv bias + eval BatchNorm (fno.py:115-117) as y = v*scale + shift
+__global__ void fold_bn_kernel(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m,
+                               const float* bn_v, float eps, int C, int Cp, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c < C) {
+    float s = bn_w[c] / sqrtf(bn_v[c] + eps);
+    scale[c] = s;
+    shift[c] = (conv_b[c] - bn_m[c]) * s + bn_b[c];
+  } else {
+    scale[c] = 0.f;
+    shift[c] = 0.f;
+  }
+}
+int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v,
+                   float eps, int C, int Cp, float* scale, float* shift, cudaStream_t st) {
+  fold_bn_kernel<<<ceil_div(Cp, 128), 128, 0, st>>>(conv_b, bn_w, bn_b, bn_m, bn_v, eps, C, Cp, scale, shift);
+  B2_LAUNCHED("fold_bn_kernel");
+  return 0;
+}
+
+__global__ void pad_copy_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int np) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) dst[i] = i < n ? src[i] : 0.f;
+}
+int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st) {
+  pad_copy_kernel<<<ceil_div(np, 256), 256, 0, st>>>(src, n, dst, np);
+  B2_LAUNCHED("pad_copy_kernel");
+  return 0;
+}
+
+}  // namespace b200fno

@@ -1,0 +1,156 @@
+"""Drop-in for ``realpdebench.model.fno`` (reference realpdebench/model/fno.py).
+
+Same class names, constructor signatures, parameter names / shapes / dtypes and
+initialisation order as the reference, so ``state_dict()`` / ``load_state_dict``
+/ ``parameters()`` and released checkpoints are interchangeable
+(checkpoint row).  ``forward`` runs on the CUDA engine.
+
+The parameters stay in the reference layout (that is what optimisers and
+checkpoints see); the engine keeps its own packed copy and refreshes it
+whenever a parameter or BatchNorm buffer changes (tensor version counters).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .engine import FNOEngine, spectral_conv
+from .model import Model
+
+
+def mse_loss(pred, target):
+    """realpdebench/utils/metrics.py:11-13 — unreduced squared error."""
+    return nn.functional.mse_loss(pred, target, reduction='none')
+
+
+class SpectralConv3d(nn.Module):
+    """fno.py:16-64.  weights1..4: complex64 [Ci,Co,m1,m2,m3], init scale*rand."""
+
+    def __init__(self, in_channels, out_channels, modes1, modes2, modes3):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.modes1, self.modes2, self.modes3 = modes1, modes2, modes3
+        self.scale = 1 / (in_channels * out_channels)
+        shape = (in_channels, out_channels, modes1, modes2, modes3)
+        for k in (1, 2, 3, 4):  # same RNG order as fno.py:31-38
+            setattr(self, f"weights{k}", nn.Parameter(self.scale * torch.rand(*shape, dtype=torch.cfloat)))
+
+    def forward(self, x):
+        return spectral_conv(x, [self.weights1, self.weights2, self.weights3, self.weights4])
+
+
+class SpectralConv2d(nn.Module):
+    """2-D analogue: weights1 (low H), weights2 (high H): complex64 [Ci,Co,m1,m2]."""
+
+    def __init__(self, in_channels, out_channels, modes1, modes2):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.modes1, self.modes2 = modes1, modes2
+        self.scale = 1 / (in_channels * out_channels)
+        for k in (1, 2):
+            setattr(self, f"weights{k}",
+                    nn.Parameter(self.scale * torch.rand(in_channels, out_channels, modes1, modes2, dtype=torch.cfloat)))
+
+    def forward(self, x):
+        return spectral_conv(x, [self.weights1, self.weights2])
+
+
+class _EngineFNO(Model):
+    """Shared host logic of FNO3d / FNO2d: parameter bookkeeping + engine dispatch."""
+
+    _ndim = 3
+
+    def _make_engine(self, impl="auto"):
+        modes = (self.modes1, self.modes2, self.modes3) if self._ndim == 3 else (self.modes1, self.modes2)
+        self._engine = FNOEngine(self._ndim, modes, self.n_layers, self.width, self.shape_in, self.shape_out,
+                                 padding=self.padding, bn_eps=self.bns[0].eps, impl=impl)
+
+    @property
+    def engine(self) -> FNOEngine:
+        return self._engine
+
+    def set_impl(self, impl: str):
+        """'auto' | 'simt' | 'tc' — which layer kernels the engine uses."""
+        self._make_engine(impl)
+
+    def _engine_state(self):
+        sd = {k: v for k, v in self.named_parameters()}
+        for i, bn in enumerate(self.bns):
+            sd[f"bns.{i}.running_mean"], sd[f"bns.{i}.running_var"] = bn.running_mean, bn.running_var
+        key = tuple((t.data_ptr(), t._version) for t in sd.values())
+        return sd, key
+
+    def _check_eval(self):
+        if self.training:
+            raise NotImplementedError(
+                "b200fno: the CUDA engine implements the eval-mode forward (BatchNorm running statistics) and the "
+                "rollout; the training forward/backward (train.py:321-334, SURVEY.md 8f row N1) is not built yet. "
+                "Call model.eval() first.")
+
+    def forward(self, x):
+        self._check_eval()
+        sd, key = self._engine_state()
+        return self._engine.forward(x, sd, key)
+
+    def rollout(self, x0, affine_a, affine_b, n_steps, out=None):
+        """Fused eval.py:313-321 loop; see realpdebench_b200.rollout for the full per-batch protocol."""
+        self._check_eval()
+        sd, key = self._engine_state()
+        return self._engine.rollout(x0, affine_a, affine_b, n_steps, sd, key, out=out)
+
+    def train_loss(self, input, target):
+        pred = self.forward(input)  # fno.py:131-133
+        return mse_loss(pred, target)
+
+
+class FNO3d(_EngineFNO):
+    """fno.py:66-143 — same constructor: FNO3d(modes1, modes2, modes3, n_layers, width, shape_in, shape_out)."""
+
+    _ndim = 3
+
+    def __init__(self, modes1, modes2, modes3, n_layers, width, shape_in, shape_out):
+        super().__init__()
+        self.modes1, self.modes2, self.modes3 = modes1, modes2, modes3
+        self.width = width
+        self.shape_in, self.shape_out = tuple(shape_in), tuple(shape_out)
+        self.dim_in = shape_in[-1]
+        self.dim_out = shape_out[-1] * shape_out[0] // shape_in[0]  # C_out * T_out / T_in (fno.py:86)
+        self.padding = 6  # fno.py:87
+        self.fc0 = nn.Linear(self.dim_in + 3, self.width)
+        self.n_layers = n_layers
+        self.spectral_convs, self.convs, self.bns = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for _ in range(n_layers):  # construction (= RNG) order of fno.py:96-100
+            self.spectral_convs.append(SpectralConv3d(width, width, modes1, modes2, modes3))
+            self.convs.append(nn.Conv3d(width, width, 1))
+            self.bns.append(nn.BatchNorm3d(width))
+        self.fc1 = nn.Linear(width, 128)
+        self.fc2 = nn.Linear(128, self.dim_out)
+        self._make_engine()
+
+
+class FNO2d(_EngineFNO):
+    """FNO-2D of SURVEY.md 8(c): FNO2d(modes1, modes2, n_layers, width, shape_in, shape_out).
+
+    Frames are folded into channels (lift feature t*C_in + c, then grid h, w;
+    projection feature t_out*C_out + c); FFT over (H, W) with two weight corners."""
+
+    _ndim = 2
+
+    def __init__(self, modes1, modes2, n_layers, width, shape_in, shape_out):
+        super().__init__()
+        self.modes1, self.modes2 = modes1, modes2
+        self.width = width
+        self.shape_in, self.shape_out = tuple(shape_in), tuple(shape_out)
+        self.dim_in = shape_in[0] * shape_in[-1]
+        self.dim_out = shape_out[0] * shape_out[-1]
+        self.padding = 6
+        self.fc0 = nn.Linear(self.dim_in + 2, self.width)
+        self.n_layers = n_layers
+        self.spectral_convs, self.convs, self.bns = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for _ in range(n_layers):
+            self.spectral_convs.append(SpectralConv2d(width, width, modes1, modes2))
+            self.convs.append(nn.Conv2d(width, width, 1))
+            self.bns.append(nn.BatchNorm2d(width))
+        self.fc1 = nn.Linear(width, 128)
+        self.fc2 = nn.Linear(128, self.dim_out)
+        self._make_engine()

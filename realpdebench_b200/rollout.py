@@ -1,0 +1,51 @@
+"""One batch of the reference evaluation loop, eval.py:296-326, on the engine.
+
+``rollout`` takes the same objects the reference script has in scope (model,
+data_normalizer, input, target, N_autoregressive) and returns what the script
+keeps: the de-normalised prediction and target (eval.py:325-326, 342-343) and
+the normalised loss term (eval.py:323).  The N-step loop with its
+postprocess / cat / preprocess glue (eval.py:313-319) is one engine call.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def rollout_affine(normalizer, c_in: int, c_out: int, device):
+    """Per-channel (a, b) with  preprocess(postprocess(p)) == p*a + b  (eval.py:316,318):
+    the model output is de-normalised with TARGET statistics and re-normalised with INPUT statistics."""
+    if hasattr(normalizer, "mean_inputs"):  # GaussianNormalizer, data_normalizer.py:50-62
+        mi, si = normalizer.mean_inputs[..., :c_out], normalizer.std_inputs[..., :c_out]
+        mt, st = normalizer.mean_targets[..., :c_out], normalizer.std_targets[..., :c_out]
+        a, b = st / si, (mt - mi) / si
+    elif hasattr(normalizer, "max_inputs"):  # RangeNormalizer, data_normalizer.py:118-130
+        a = normalizer.max_targets[..., :c_out] / normalizer.max_inputs[..., :c_out]
+        b = torch.zeros_like(a)
+    else:  # IdentityNormalizer
+        a, b = torch.ones(c_out), torch.zeros(c_out)
+    return (a.to(device=device, dtype=torch.float32).reshape(-1).contiguous(),
+            b.to(device=device, dtype=torch.float32).reshape(-1).contiguous())
+
+
+def rollout(model, data_normalizer, input, target, N_autoregressive: int, unmeasured_c=None):
+    """Returns ``(pred, target, normalized_loss, unmeasured_c)`` for one batch.
+
+    * ``pred``, ``target``: de-normalised tensors on the device (eval.py:325-326)
+    * ``normalized_loss``: python float added to ``normalized_test_loss`` (eval.py:323)
+    * ``unmeasured_c``: all-zero target channels, computed on the first batch
+      like eval.py:298-302 and passed back in for the following ones.
+    """
+    b = input.size(0)
+    if unmeasured_c is None:
+        unmeasured_c = sum(int(torch.all(target[..., c_] == 0)) for c_ in range(target.shape[-1]))
+    c = target.shape[-1] - unmeasured_c
+    c_in, c_out = input.shape[-1], target.shape[-1]
+    with torch.no_grad():
+        input, target = data_normalizer.preprocess(input, target)  # eval.py:311 (H2D + affine)
+        a, bb = rollout_affine(data_normalizer, c_in, c_out, input.device)
+        pred = model.rollout(input, a, bb, N_autoregressive)  # eval.py:313-322, parameter channels already dropped
+        loss = torch.nn.functional.mse_loss(pred[..., :c], target[..., :c], reduction='none') \
+            .reshape(b, -1).mean().item()  # eval.py:323
+        _, pred = data_normalizer.postprocess(input, pred)  # eval.py:325
+        _, target = data_normalizer.postprocess(input, target)  # eval.py:326
+    return pred, target, loss, unmeasured_c

@@ -1,0 +1,197 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle and the
+committed golden vectors.  Tolerance: relative L2 <= 1e-5 in fp32 (BASELINE.json
+north_star) for one forward; chained rollouts are gated per step (teacher forced)
+at 1e-5 and end to end at a looser bound because fp32 differences are re-fed."""
+import pytest
+import torch
+
+from oracle import fno_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def R():
+    import realpdebench_b200 as R
+    from realpdebench_b200 import _capi
+    _capi.lib()  # fail loudly if the CUDA library is missing
+    return R
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def make3d(R, ctor, sd):
+    m = R.FNO3d(*ctor)
+    m.load_state_dict(sd)
+    return m.to(dev()).eval()
+
+
+# ---------------------------------------------------------------- spectral operator
+def test_kat_b_spectral_conv(R, golden):
+    g = golden("kat_b.pt")
+    s = R.SpectralConv3d(4, 5, 2, 3, 4)
+    with torch.no_grad():
+        for k in range(4):
+            getattr(s, f"weights{k + 1}").copy_(g["w"][k])
+    o = s.to(dev())(g["z"].to(dev())).cpu()
+    assert o.shape == (2, 5, 9, 10, 12)
+    assert O.rel_l2(o, g["o"]) < TOL
+    assert abs(o.sum().item() - 8.836092) < 1e-3
+
+
+@pytest.mark.parametrize("shape,modes,ci,co", [
+    ((8, 7, 16), (3, 2, 9), 3, 3),     # Nyquist bin kept
+    ((5, 6, 7), (3, 4, 4), 2, 4),      # overlapping corners, odd sizes
+    ((26, 70, 134), (4, 12, 16), 8, 8),  # cylinder padded grid
+])
+def test_spectral_conv3d_vs_oracle(R, shape, modes, ci, co):
+    torch.manual_seed(0)
+    x = torch.randn(2, ci, *shape)
+    ws = [torch.randn(ci, co, *modes, dtype=torch.cfloat) / (ci * co) ** 0.5 for _ in range(4)]
+    ref = O.spectral_conv3d(x.double(), *[w.to(torch.cdouble) for w in ws])
+    from realpdebench_b200.engine import spectral_conv
+    got = spectral_conv(x.to(dev()), [w.to(dev()) for w in ws]).cpu()
+    assert O.rel_l2(got, ref) < TOL
+    # and not worse than torch's own fp32 FFT path by more than the tolerance
+    assert O.rel_l2(got, O.spectral_conv3d(x, *ws)) < TOL
+
+
+def test_spectral_conv2d_golden_mwt(R, golden):
+    g = golden("spectral2d.pt")
+    from realpdebench_b200.engine import spectral_conv
+    y = spectral_conv(g["x"].to(dev()), [g["w1"].to(dev()), g["w2"].to(dev())]).cpu()
+    assert O.rel_l2(y, g["y"]) < TOL
+
+
+def test_spectral_conv2d_full_size_linearity(R):
+    """BASELINE config C2 grid (262x518 padded), size-independent property: the operator is linear."""
+    torch.manual_seed(3)
+    from realpdebench_b200.engine import spectral_conv
+    ws = [(torch.randn(16, 16, 12, 16, dtype=torch.cfloat) / 16).to(dev()) for _ in range(2)]
+    x, y = torch.randn(1, 16, 262, 518, device=dev()), torch.randn(1, 16, 262, 518, device=dev())
+    lhs = spectral_conv(2.5 * x - 0.75 * y, ws)
+    rhs = 2.5 * spectral_conv(x, ws) - 0.75 * spectral_conv(y, ws)
+    assert O.rel_l2(lhs, rhs) < TOL
+    # one sample also against torch's FFT on the GPU (same math as the oracle, other device)
+    assert O.rel_l2(spectral_conv(x, ws), O.spectral_conv2d(x, *ws)) < TOL
+
+
+# ---------------------------------------------------------------- whole network
+def test_kat_a_forward(R, golden):
+    g = golden("kat_a.pt")
+    m = make3d(R, g["ctor"], g["sd"])
+    y = m(g["x"].to(dev())).cpu()
+    assert O.rel_l2(y, g["y"]) < TOL
+    assert abs(y.sum().item() - (-1280.620483)) < 2e-2
+    assert torch.allclose(y[0, 0, 0, 0], torch.tensor([-0.16739486, 0.09012541, -0.03944759]), atol=2e-6)
+
+
+def test_odd_sizes_width6_r2(R, golden):
+    g = golden("fno3d_odd.pt")
+    m = make3d(R, g["ctor"], g["sd"])
+    y = m(g["x"].to(dev())).cpu()
+    assert y.shape == g["y_eval"].shape
+    assert O.rel_l2(y, g["y_eval"]) < TOL
+
+
+def test_train_mode_fails_loudly(R, golden):
+    g = golden("fno3d_odd.pt")
+    m = make3d(R, g["ctor"], g["sd"]).train()
+    with pytest.raises(NotImplementedError):
+        m(g["x"].to(dev()))
+
+
+def test_cylinder_config_forward(R):
+    """configs/cylinder/fno.yaml hyper-parameters on a 64x64x2ch input (BASELINE config #1 shape)."""
+    torch.manual_seed(0)
+    s = (20, 64, 64, 2)
+    sd = O.init_state(3, (4, 12, 16), 4, 64, s, s)
+    O.randomize_bn(sd)
+    m = make3d(R, (4, 12, 16, 4, 64, s, s), sd)
+    x = torch.randn(2, *s)
+    y = m(x.to(dev())).cpu()
+    assert O.rel_l2(y, O.fno3d_forward(sd, x, s)) < TOL
+
+
+def test_variable_batch_and_weight_update(R, golden):
+    g = golden("kat_a.pt")
+    m = make3d(R, g["ctor"], g["sd"])
+    x = g["x"].to(dev())
+    y2 = m(x)
+    y1 = m(x[:1])  # smaller batch on the same plan (last DataLoader batch, eval.py:264)
+    assert torch.equal(y1, y2[:1])
+    xx = torch.cat([x, x, x], 0)  # larger batch -> re-plan
+    assert torch.equal(m(xx)[4:5], y2[:1])
+    with torch.no_grad():
+        m.fc2.bias.add_(1.0)  # in-place parameter update must invalidate the packed copy
+    assert torch.allclose(m(x), y2 + 1.0, atol=1e-5)
+
+
+def test_fno2d_forward(R):
+    torch.manual_seed(5)
+    s = (5, 30, 44, 3)
+    sd = O.init_state(2, (7, 9), 3, 32, s, s)
+    O.randomize_bn(sd, 11)
+    m = R.FNO2d(7, 9, 3, 32, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    x = torch.randn(3, *s)
+    y = m(x.to(dev())).cpu()
+    assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
+
+
+def test_fno2d_bench_shape_batch_consistency(R):
+    """C2 model (FNO-2D 256x512, 20 frames x 3 ch, modes 12x16, width 64, 4 layers): one sample vs the oracle,
+    and batch sharding (what the multi-GPU path relies on): rows of a batched forward == single forwards."""
+    torch.manual_seed(6)
+    s = (20, 256, 512, 3)
+    sd = O.init_state(2, (12, 16), 4, 64, s, s)
+    O.randomize_bn(sd)
+    m = R.FNO2d(12, 16, 4, 64, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    x = torch.randn(2, *s)
+    y = m(x.to(dev()))
+    assert O.rel_l2(y[:1].cpu(), O.fno2d_forward(sd, x[:1], s)) < TOL
+    assert torch.equal(m(x[1:].to(dev())), y[1:])
+
+
+# ---------------------------------------------------------------- rollout
+@pytest.mark.parametrize("case", ["plain", "controlled", "range"])
+def test_rollout_golden(R, golden, case):
+    g = golden("rollout.pt")[case]
+    m = make3d(R, g["ctor"], g["sd"])
+    norm = O.Normalizer(g["kind"], device=dev(), **g["stats"])
+    pred, tgt, loss, _ = R.rollout(m, norm, g["input"].to(dev()), g["target"].to(dev()), g["n_auto"])
+    assert pred.shape == g["pred"].shape
+    assert O.rel_l2(pred.cpu(), g["pred"]) < 5e-5  # three chained steps
+    assert O.rel_l2(tgt.cpu(), g["target_dn"]) < 1e-6
+    assert abs(loss - g["loss"]) < 1e-4 * max(1.0, abs(g["loss"]))
+    # teacher forced: each step from the reference's own state
+    c_in, c_out = g["input"].shape[-1], g["target"].shape[-1]
+    a, b = R.rollout_affine(norm, c_in, c_out, dev())
+    for i in range(g["n_auto"]):
+        step = m.rollout(g["states"][i].to(dev()), a, b, 1).cpu()
+        assert O.rel_l2(step, g["states"][i + 1][..., :c_out]) < TOL
+
+
+def test_rollout_is_graph_capturable(R, golden):
+    g = golden("rollout.pt")["controlled"]
+    m = make3d(R, g["ctor"], g["sd"])
+    norm = O.Normalizer(g["kind"], device=dev(), **g["stats"])
+    a, b = R.rollout_affine(norm, 5, 3, dev())
+    x0 = norm.preprocess(g["input"].to(dev()), g["target"].to(dev()))[0]
+    eager = m.rollout(x0, a, b, 3)
+    out = torch.empty_like(eager)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        m.rollout(x0, a, b, 3, out=out)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)

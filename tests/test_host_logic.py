@@ -1,0 +1,143 @@
+"""CPU tests of the host side: C-ABI surface, module/state_dict contract, registry drop-in."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import fno_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200fno.h")
+
+
+def test_library_exports_every_declared_symbol():
+    from realpdebench_b200 import _capi
+    lib = _capi.lib()
+    text = open(HEADER).read()
+    declared = set(re.findall(r"\b(b200fno_[a-z_0-9]+)\s*\(", text))
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.b200fno_abi_version() == _capi.ABI_VERSION
+
+
+def test_header_is_plain_c_and_struct_layout_matches_binding(tmp_path):
+    from realpdebench_b200 import _capi
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "b200fno.h"\nint main(void){printf("%zu %zu %zu\\n",'
+                   'sizeof(b200fno_desc_t),sizeof(b200fno_weights_t),offsetof(b200fno_desc_t,bn_eps));return 0;}\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_capi.Desc)
+    assert int(out[1]) == ctypes.sizeof(_capi.Weights)
+    assert int(out[2]) == _capi.Desc.bn_eps.offset
+
+
+def test_no_device_errors_are_reported_not_crashed():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    from realpdebench_b200 import _capi
+    lib = _capi.lib()
+    d = _capi.Desc(abi_version=1, ndim=3, max_batch=1, t_in=4, t_out=4, h=8, w=8, c_in=2, c_out=2, width=8,
+                   n_layers=1, modes1=2, modes2=2, modes3=2, padding=6, proj_hidden=128, bn_eps=1e-5)
+    plan = ctypes.c_void_p()
+    rc = lib.b200fno_plan_create(ctypes.byref(d), ctypes.byref(plan))
+    assert rc == -3 and b"CUDA" in lib.b200fno_last_error()
+    d.ndim = 4
+    assert lib.b200fno_plan_create(ctypes.byref(d), ctypes.byref(plan)) == -1
+
+
+def test_module_matches_reference_state_dict_and_init(golden):
+    import realpdebench_b200 as R
+    g = golden("kat_a.pt")
+    torch.manual_seed(0)
+    m = R.FNO3d(*g["ctor"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["sd"].keys())
+    for k, v in g["sd"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+        if ".bns." not in "." + k:
+            assert torch.equal(sd[k], v), k  # same RNG order as fno.py:89-103
+    assert sum(p.numel() for p in m.parameters()) == sum(
+        v.numel() for k, v in g["sd"].items() if "running" not in k and "num_batches" not in k)
+    m.load_state_dict(g["sd"])
+
+
+def test_cpu_forward_fails_loudly_no_fallback(golden):
+    import realpdebench_b200 as R
+    g = golden("kat_a.pt")
+    m = R.FNO3d(*g["ctor"]).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(g["x"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        R.SpectralConv3d(2, 2, 1, 1, 1)(torch.randn(1, 2, 4, 4, 4))
+
+
+def test_fno2d_module_contract():
+    import realpdebench_b200 as R
+    torch.manual_seed(4)
+    s = (3, 10, 12, 2)
+    m = R.FNO2d(4, 5, 2, 8, s, s)
+    torch.manual_seed(4)
+    sd = O.init_state(2, (4, 5), 2, 8, s, s)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_rollout_affine_is_post_then_pre():
+    from realpdebench_b200 import rollout_affine
+    for kind in ("gaussian", "range", "none"):
+        n = O.synthetic_normalizer(5, 3, kind=kind)
+        a, b = rollout_affine(n, 5, 3, "cpu")
+        p = torch.randn(2, 4, 3)
+        x = torch.randn(2, 4, 5)
+        want = n.preprocess(n.postprocess(x, p)[1], p)[0]
+        assert torch.allclose(p * a + b, want, atol=1e-6)
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_install_serves_unmodified_reference_registry():
+    code = r'''
+import sys, types, torch
+for n in ("matplotlib", "matplotlib.pyplot", "h5py"):
+    sys.modules.setdefault(n, types.ModuleType(n))
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import realpdebench_b200 as R
+R.install()
+from realpdebench.model.load_model import load_model
+import yaml, os
+cfg = yaml.safe_load(open(os.path.join(%r, "realpdebench/configs/cylinder/fno.yaml")))
+ds = [(torch.zeros(20, 16, 16, 3), torch.zeros(20, 16, 16, 3))]
+torch.manual_seed(0)
+m = load_model(ds, "cpu", **cfg)
+assert type(m).__module__ == "realpdebench_b200.fno", type(m)
+from realpdebench.model.model import Model
+assert isinstance(m, Model)
+cfg["model_name"] = "fno2d"
+m2 = load_model(ds, "cpu", **cfg)
+assert type(m2).__name__ == "FNO2d" and m2.modes1 == cfg["modes2"] and m2.modes2 == cfg["modes3"]
+R.uninstall()
+from realpdebench.model.fno import FNO3d as RefFNO
+assert RefFNO.__module__ == "realpdebench.model.fno"
+torch.manual_seed(0)
+ref = RefFNO(4, 12, 16, 4, 64, (20, 16, 16, 3), (20, 16, 16, 3))
+a, b = m.state_dict(), ref.state_dict()
+assert list(a) == list(b)
+assert all(torch.equal(a[k], b[k]) for k in a)
+try:
+    load_model(ds, "cpu", model_name="nope")
+except ValueError as e:
+    assert "not supported" in str(e)
+print("OK")
+''' % (REF, ROOT, REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
