@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: FNO autoregressive-rollout field-points/sec (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # engine arm
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port on host cores)
+
+Workload (BASELINE.json configs[1]): FNO-2D, synthetic cylinder-shaped
+grid 256x512, 20 input frames x 3 channels, modes (12,16), width 64, 4 layers, fp32,
+batch 8 per GPU, 20-step autoregressive rollout with Gaussian (de/re)normalisation.
+One "step" = one 20-step rollout of one batch; one field-point = one predicted (b, t, h, w).
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement):
+  value     device-resident rollout (inputs already in HBM), CUDA-event timed, max over ranks
+  e2e       the same through realpdebench_b200.rollout() with pinned HOST input/target:
+            H2D copies + normalisation + rollout + normalised loss read back every step
+  roofline  dominant kernel (the fused Fourier-layer kernel) vs the measured HBM peak
+  cpu_baseline  the oracle port (torch CPU, all host threads) on a bounded sample, rank 0, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (ndim, modes, n_layers, width, shape_in, shape_out, batch per GPU, n_autoregressive)
+    "fno2d_cylinder_256x512_rollout20": (2, (12, 16), 4, 64, (20, 256, 512, 3), (20, 256, 512, 3), 8, 20),
+    "fno3d_cylinder_64x128_rollout10": (3, (4, 12, 16), 4, 64, (20, 64, 128, 3), (20, 64, 128, 3), 16, 10),
+}
+DEFAULT_WORKLOAD = "fno2d_cylinder_256x512_rollout20"
+METRIC = "fno_rollout_field_points_per_sec"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.thread.join(timeout=5)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        load = [s for s in sm if s >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_state(ndim, modes, n_layers, width, s_in, s_out):
+    """Reference-initialised weights (seed 0) + randomised BN statistics (SURVEY 8d synthetic inputs)."""
+    from oracle import fno_oracle as O  # parameter initialisation recipe only (not on the timed path)
+    torch.manual_seed(0)
+    sd = O.init_state(ndim, modes, n_layers, width, s_in, s_out)
+    O.randomize_bn(sd)
+    return sd
+
+
+def synthetic_stats(c_in, c_out):
+    g = torch.Generator().manual_seed(4321)
+    mi, si = torch.randn(c_in, generator=g) * 0.1, torch.rand(c_in, generator=g) + 0.5
+    mt, st = torch.randn(c_out, generator=g) * 0.1, torch.rand(c_out, generator=g) + 0.5
+    return dict(mean_inputs=mi, std_inputs=si, mean_targets=mt, std_targets=st)
+
+
+class GaussianStats:
+    """Normaliser object with the reference protocol (data_normalizer.py:20-62), stats given directly."""
+
+    def __init__(self, device, mean_inputs, std_inputs, mean_targets, std_targets):
+        self.device = device
+        self.mean_inputs, self.std_inputs = mean_inputs.to(device), std_inputs.to(device)
+        self.mean_targets, self.std_targets = mean_targets.to(device), std_targets.to(device)
+
+    def preprocess(self, x, y):
+        c1, c2 = x.shape[-1], y.shape[-1]
+        x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+        return (x - self.mean_inputs[..., :c1]) / self.std_inputs[..., :c1], \
+               (y - self.mean_targets[..., :c2]) / self.std_targets[..., :c2]
+
+    def postprocess(self, x, y):
+        c1, c2 = x.shape[-1], y.shape[-1]
+        x, y = x.to(self.device), y.to(self.device)
+        return x * self.std_inputs[..., :c1] + self.mean_inputs[..., :c1], \
+               y * self.std_targets[..., :c2] + self.mean_targets[..., :c2]
+
+
+def cpu_reference_sample(wl, steps, warmup, n_auto_sample=1, batch=1):
+    """The oracle port (torch CPU ops == the reference's arithmetic) on a bounded sample of the workload."""
+    from oracle import fno_oracle as O
+    ndim, modes, L, width, s_in, s_out, _, _ = WORKLOADS[wl]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = build_state(ndim, modes, L, width, s_in, s_out)
+    fwd = (lambda t: O.fno3d_forward(sd, t, s_out)) if ndim == 3 else (lambda t: O.fno2d_forward(sd, t, s_out))
+    norm = O.Normalizer("gaussian", **synthetic_stats(s_in[-1], s_out[-1]))
+    torch.manual_seed(1234)
+    x = torch.randn(batch, *s_in)
+    tgt = torch.randn(batch, n_auto_sample * s_out[0], *s_out[1:])
+    pts = batch * n_auto_sample * s_out[0] * s_out[1] * s_out[2]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.rollout(fwd, norm, x, tgt, n_auto_sample)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": pts / (ms * 1e-3), "unit": "field-points/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/fno_oracle.py rollout, batch {batch}, {n_auto_sample} autoregressive step(s) of "
+                      f"{wl}, mean of {steps} run(s) after {warmup} warm-up, torch {torch.__version__} CPU "
+                      f"{cores} threads", "ms_per_sample": ms}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    ndim, modes, L, width, s_in, s_out, B, n_auto = WORKLOADS[wl]
+    base = cpu_reference_sample(wl, max(1, args.steps), max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "field-points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_sample"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl, args.gpus), "cpu_baseline": {k: base[k] for k in
+                                                                        ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "field-points/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, n_gpus):
+    ndim, modes, L, width, s_in, s_out, B, n_auto = WORKLOADS[wl]
+    return {"workload": wl, "operator": f"fno{ndim}d", "modes": list(modes), "width": width, "n_layers": L,
+            "shape_in": list(s_in), "shape_out": list(s_out), "batch_per_gpu": B, "global_batch": B * n_gpus,
+            "n_autoregressive": n_auto, "normalizer": "gaussian", "parallelism": f"batch-sharded x{n_gpus}, "
+            "no data-path collective", "l2_policy": "working set per layer (2 x 278 MB activations) exceeds the "
+            "126 MB L2; no explicit flush"}
+
+
+def run_engine(args):
+    import realpdebench_b200 as R
+    from realpdebench_b200 import _capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = args.workload
+    ndim, modes, L, width, s_in, s_out, B, n_auto = WORKLOADS[wl]
+    if args.batch:
+        B = args.batch
+    if args.n_auto:
+        n_auto = args.n_auto
+    sd = build_state(ndim, modes, L, width, s_in, s_out)
+    model = (R.FNO3d(*modes, L, width, s_in, s_out) if ndim == 3 else R.FNO2d(*modes, L, width, s_in, s_out))
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    if args.engine_impl != "auto":
+        model.set_impl(args.engine_impl)
+    norm = GaussianStats(dev, **synthetic_stats(s_in[-1], s_out[-1]))
+    c_in, c_out = s_in[-1], s_out[-1]
+    a, b = R.rollout_affine(norm, c_in, c_out, dev)
+
+    torch.manual_seed(1234 + rank)
+    x_host = torch.randn(B, *s_in).pin_memory()
+    tgt_host = torch.randn(B, n_auto * s_out[0], *s_out[1:]).pin_memory()
+    x0 = norm.preprocess(x_host, tgt_host[:, :1])[0].contiguous()
+    pred = torch.empty(B, n_auto * s_out[0], *s_out[1:], device=dev)
+    pts_per_step = B * n_auto * s_out[0] * s_out[1] * s_out[2]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident arm ("value") ----------------
+    for _ in range(max(3, args.warmup)):
+        model.rollout(x0, a, b, n_auto, out=pred)
+    barrier()
+    _capi.lib().b200fno_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            model.rollout(x0, a, b, n_auto, out=pred)
+        e1.record()
+        barrier()
+    launches = int(_capi.lib().b200fno_launch_count())
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * pts_per_step / (ms_step * 1e-3)
+
+    # ---------------- per-stage timing pass (roofline of the dominant kernel) ----------------
+    eng = model.engine
+    eng.timing(True)
+    model.rollout(x0, a, b, n_auto, out=pred)
+    torch.cuda.synchronize()
+    stages = eng.timing_collect()
+    eng.timing(False)
+    peak, peak_src = measured_peaks()
+    roofline = None
+    if "layer" in stages:
+        hp, wp = s_in[1] + 6, s_in[2] + 6
+        tp = s_in[0] + 6 if ndim == 3 else 1
+        bytes_launch = 2.0 * B * tp * hp * wp * width * 4  # per layer, activation in + out
+        dur = stages["layer"]["ms"] / stages["layer"]["launches"] * 1e-3
+        ach = bytes_launch / dur / 1e9
+        roofline = {"bound": "hbm", "kernel": "fused Fourier-layer kernel (bypass conv + inverse-W DFT + BN + GELU)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
+                    "avg_launch_ms": dur * 1e3}
+    alg_bytes_step = n_auto * eng.algorithmic_bytes(B)
+    whole = {"algorithmic_bytes_per_step": alg_bytes_step, "achieved_gbs": alg_bytes_step / (ms_step * 1e-3) / 1e9,
+             "frac_of_hbm_peak": alg_bytes_step / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---------------- end-to-end arm: public API with host buffers ----------------
+    def e2e_step():
+        return R.rollout(model, norm, x_host, tgt_host, n_auto, unmeasured_c=0)
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    loss = 0.0
+    for _ in range(e2e_steps):
+        _, _, l, _ = e2e_step()
+        loss += l
+    f1.record()
+    barrier()
+    e2e_ms = reduce_max(f0.elapsed_time(f1)) / e2e_steps
+    e2e = {"value": world * pts_per_step / (e2e_ms * 1e-3), "unit": "field-points/s",
+           "h2d_bytes_per_step": x_host.numel() * 4 + tgt_host.numel() * 4, "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "realpdebench_b200.rollout(model, data_normalizer, input, target, N_autoregressive)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_sample(wl, 2, 1)
+        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "field-points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
+                "impl": "b200fno", "engine_impl": args.engine_impl, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks.summary(), "roofline": roofline, "whole_step": whole,
+                "stages_ms_per_rollout": {k: round(v["ms"], 4) for k, v in stages.items()},
+                "cpu_baseline": cpu_baseline, "normalized_loss_check": loss / e2e_steps}
+        if args.batch or args.n_auto:
+            line["config"]["batch_per_gpu"], line["config"]["n_autoregressive"] = B, n_auto
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200fno", choices=["b200fno", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--engine-impl", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--batch", type=int, default=0, help="override batch per GPU (not the headline config)")
+    ap.add_argument("--n-auto", type=int, default=0, help="override rollout length (not the headline config)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

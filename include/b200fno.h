@@ -155,6 +155,14 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
 /* Kernels launched by this library on this thread since the last reset. */
 int64_t b200fno_launch_count(void);
 void b200fno_launch_count_reset(void);
+/* Per-stage device timing: when enabled, every stage launch of forward/rollout is
+ * bracketed by CUDA events on the caller's stream (not graph-capturable while on).
+ * collect() waits for the recorded events and returns, per stage, the summed
+ * milliseconds and the number of launches since enable()/the last collect().
+ * Stage order: lift, fwdW, fwdH, fwdT, modes, invT, invH, layer, proj. */
+#define B200FNO_NUM_STAGES 9
+int b200fno_timing_enable(b200fno_plan_t* plan, int on);
+int b200fno_timing_collect(b200fno_plan_t* plan, double* ms /*[9]*/, int64_t* count /*[9]*/);
 /* Host copy of truncated-DFT table `which` (0 fwdW, 1 fwdH, 2 fwdT, 3 invT, 4 invH,
  * 5 invW) for a transformed grid (t,h,w) -- the values the kernels multiply by.
  * Needs no device.  Writes at most `cap` floats to `out`, the row pitch to *ld and

@@ -19,7 +19,8 @@ SYMBOLS = (
     "b200fno_plan_set_impl", "b200fno_plan_get_impl", "b200fno_plan_workspace_bytes", "b200fno_plan_packed_bytes",
     "b200fno_plan_bind", "b200fno_pack_weights", "b200fno_forward", "b200fno_rollout",
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
-    "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes",
+    "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
+    "b200fno_timing_collect",
 )
 
 
@@ -90,12 +91,19 @@ def lib() -> C.CDLL:
     L.b200fno_host_table.restype = i64
     L.b200fno_host_table.argtypes = [i32] * 8 + [C.POINTER(C.c_float), i64, C.POINTER(i32), C.POINTER(i32),
                                                  C.POINTER(i32)]
+    L.b200fno_timing_enable.restype = C.c_int
+    L.b200fno_timing_enable.argtypes = [vp, C.c_int]
+    L.b200fno_timing_collect.restype = C.c_int
+    L.b200fno_timing_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.b200fno_algorithmic_bytes.restype = C.c_double
     L.b200fno_algorithmic_bytes.argtypes = [vp, i32]
     if L.b200fno_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.b200fno_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L
     return L
+
+
+STAGES = ("lift", "fwdW", "fwdH", "fwdT", "modes", "invT", "invH", "layer", "proj")
 
 
 def check(rc: int) -> None:

@@ -24,6 +24,43 @@ int64_t& launch_counter() { return g_launches; }
 
 using namespace b200fno;
 
+// Optional per-stage CUDA-event timing (bench.py's roofline numbers are measured with this,
+// on the caller's stream, around the real launches).
+enum Stage { ST_LIFT = 0, ST_FWD_W, ST_FWD_H, ST_FWD_T, ST_MODES, ST_INV_T, ST_INV_H, ST_LAYER, ST_PROJ, ST_COUNT };
+struct Timing {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<int> stage;
+  size_t used = 0;
+  ~Timing() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+struct StageScope {
+  Timing* t;
+  cudaStream_t st;
+  size_t slot = (size_t)-1;
+  StageScope(Timing* t_, int stage, cudaStream_t s) : t(t_), st(s) {
+    if (!t || !t->enabled) return;
+    if (t->used + 2 > t->ev.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        t->ev.push_back(e);
+      }
+      t->stage.push_back(stage);
+    } else {
+      t->stage[t->used / 2] = stage;
+    }
+    slot = t->used;
+    t->used += 2;
+    cudaEventRecord(t->ev[slot], st);
+  }
+  ~StageScope() {
+    if (slot != (size_t)-1) cudaEventRecord(t->ev[slot + 1], st);
+  }
+};
+
 struct LayerPacked {
   float *convT, *scale, *shift, *spec;
 };
@@ -48,6 +85,7 @@ struct b200fno_plan {
   float* packed = nullptr;
   size_t packed_bytes = 0;
   bool weights_ready = false;
+  Timing timing;
   // views into ws / packed
   float *act[2], *bufAD, *bufBC, *bufS, *bufO;
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
@@ -84,30 +122,42 @@ static size_t spectral_scratch_floats(const Geom& g, int B) {
 //   act -> D   (everything of SpectralConv3d.forward except the last inverse-W stage,
 //               which the layer kernel fuses with the bypass conv)
 static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
-                        float* bufBC, float* bufS, float* bufO, cudaStream_t st) {
+                        float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr) {
   const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
-  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
-  B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD, (long long)g.K2 * g.Cp,
-                     g.Cp, g.Cp, B * g.Tp * g.Hp, st));
-  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
-  float* fwdH_out = g.ndim == 3 ? bufBC : bufS;
-  B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
-                     2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
+    StageScope sc(tm, ST_FWD_W, st);
+    B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD,
+                       (long long)g.K2 * g.Cp, g.Cp, g.Cp, B * g.Tp * g.Hp, st));
+  }
+  {  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
+    StageScope sc(tm, ST_FWD_H, st);
+    float* fwdH_out = g.ndim == 3 ? bufBC : bufS;
+    B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
+                       2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  }
   if (g.ndim == 3) {
+    StageScope sc(tm, ST_FWD_T, st);
     const long long n_t = (long long)g.KH * n_hw;
     B2_TRY(launch_lmul(tab.LT, tab.ldLT, 2 * g.KT, 2 * g.Tp, bufBC, (long long)g.Tp * 2 * n_t, n_t, bufS,
                        2LL * g.KT * n_t, n_t, (int)n_t, B, st));
   }
-  B2_TRY(launch_modes(bufS, Wpk, bufO, B, g.NM, g.Cp, st));
+  {
+    StageScope sc(tm, ST_MODES, st);
+    B2_TRY(launch_modes(bufS, Wpk, bufO, B, g.NM, g.Cp, st));
+  }
   const float* invH_in = bufO;
   if (g.ndim == 3) {
+    StageScope sc(tm, ST_INV_T, st);
     const long long n_t = (long long)g.KH * n_hw;
     B2_TRY(launch_lmul(tab.LTi, tab.ldLTi, 2 * g.Tp, 2 * g.KT, bufO, 2LL * g.KT * n_t, n_t, bufBC,
                        (long long)g.Tp * 2 * n_t, n_t, (int)n_t, B, st));
     invH_in = bufBC;
   }
-  B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
-                     (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  {
+    StageScope sc(tm, ST_INV_H, st);
+    B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
+                       (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+  }
   return 0;
 }
 
@@ -357,14 +407,20 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   la.c_in = d.c_in, la.Fin = p->Fin, la.ng = p->ng, la.Klp = p->Klp;
   la.x_sB = (long long)d.t_in * d.h * d.w * d.c_in;
   la.x_sT = d.ndim == 3 ? (long long)d.h * d.w * d.c_in : 0;
-  B2_TRY(launch_lift(la, st));
+  {
+    StageScope sc(&p->timing, ST_LIFT, st);
+    B2_TRY(launch_lift(la, st));
+  }
   int cur = 0;
   const long long rows = (long long)B * g.Tp * g.Hp;
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerPacked& L = p->layers[l];
-    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st));
-    B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows, g.Wp,
-                        g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
+    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing));
+    {
+      StageScope sc(&p->timing, ST_LAYER, st);
+      B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows, g.Wp,
+                          g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
+    }
     cur ^= 1;
   }
   *final_act = p->act[cur];
@@ -386,6 +442,7 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a
   pa.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
   pa.st_sB = (long long)d.t_in * HW * d.c_in;
   pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
+  StageScope sc(&p->timing, ST_PROJ, st);
   return launch_proj(pa, st);
 }
 
@@ -511,6 +568,28 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
     rc = B200FNO_ECUDA;
   }
   return rc;
+}
+
+int b200fno_timing_enable(b200fno_plan_t* p, int on) {
+  if (!p) return B200FNO_EINVAL;
+  p->timing.enabled = on != 0;
+  p->timing.used = 0;
+  return 0;
+}
+
+int b200fno_timing_collect(b200fno_plan_t* p, double* ms, int64_t* count) {
+  if (!p || !ms || !count) return B200FNO_EINVAL;
+  for (int i = 0; i < ST_COUNT; ++i) ms[i] = 0.0, count[i] = 0;
+  Timing& t = p->timing;
+  for (size_t s = 0; s + 1 < t.used; s += 2) {
+    B2_CUDA(cudaEventSynchronize(t.ev[s + 1]));
+    float f = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&f, t.ev[s], t.ev[s + 1]));
+    ms[t.stage[s / 2]] += f;
+    count[t.stage[s / 2]] += 1;
+  }
+  t.used = 0;
+  return 0;
 }
 
 int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,

@@ -160,6 +160,16 @@ class FNOEngine:
                                               stream))
         return out
 
+    def timing(self, on: bool) -> None:
+        """Bracket every stage launch with CUDA events (bench.py's per-kernel roofline numbers)."""
+        check(_capi.lib().b200fno_timing_enable(self._plan, int(on)))
+
+    def timing_collect(self) -> dict:
+        ms = (C.c_double * len(_capi.STAGES))()
+        cnt = (C.c_int64 * len(_capi.STAGES))()
+        check(_capi.lib().b200fno_timing_collect(self._plan, ms, cnt))
+        return {s: {"ms": ms[i], "launches": cnt[i]} for i, s in enumerate(_capi.STAGES) if cnt[i]}
+
     def algorithmic_bytes(self, batch: int) -> float:
         return float(_capi.lib().b200fno_algorithmic_bytes(self._plan, batch))
 
