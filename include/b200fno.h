@@ -163,6 +163,14 @@ void b200fno_launch_count_reset(void);
 #define B200FNO_NUM_STAGES 9
 int b200fno_timing_enable(b200fno_plan_t* plan, int on);
 int b200fno_timing_collect(b200fno_plan_t* plan, double* ms /*[9]*/, int64_t* count /*[9]*/);
+/* Tensor-core primitive self-test: one CTA computes D[128][N] = A * B^T with tcgen05.mma kind::tf32.
+ *   mode_a: 0 A[128][K] staged by threads (manual 128B swizzle), 1 same via TMA, 2 A given as [K][128]
+ *           (MN-major) via TMA, 3 A[128][K] placed in TMEM (tcgen05.st) -- the .ts MMA form
+ *   mode_b: 0 B[N][K] manual, 1 B[N][K] via TMA, 2 B given as [K][N] (MN-major) via TMA
+ *   out_tma: 0 D written with st.global, 1 through a swizzled staging tile + TMA store
+ * N in {32,64,128}, K in {32,64,96,128}; all pointers device fp32. */
+int b200fno_selftest_umma(int32_t mode_a, int32_t mode_b, int32_t out_tma, int32_t N, int32_t K, const float* A,
+                          const float* B, float* D, void* stream);
 /* Host copy of truncated-DFT table `which` (0 fwdW, 1 fwdH, 2 fwdT, 3 invT, 4 invH,
  * 5 invW) for a transformed grid (t,h,w) -- the values the kernels multiply by.
  * Needs no device.  Writes at most `cap` floats to `out`, the row pitch to *ld and
