@@ -6,8 +6,18 @@
 #include <new>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200fno {
+
+// tc_layer.cu
+bool tc_layer_supported(const Geom& g);
+int tc_make_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g);
+int tc_make_w_map(CUtensorMap* m, const float* w_hl);
+int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g);
+int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
+                    const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
+                    cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -63,6 +73,8 @@ struct StageScope {
 
 struct LayerPacked {
   float *convT, *scale, *shift, *spec;
+  float* convHL;  // [2][Cp][Cp]: conv weight [o][i] as 3xTF32 hi | lo planes (tensor-core path)
+  CUtensorMap tmW;
 };
 
 struct b200fno_plan {
@@ -90,6 +102,9 @@ struct b200fno_plan {
   float *act[2], *bufAD, *bufBC, *bufS, *bufO;
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
   std::vector<LayerPacked> layers;
+  // tensor-core path
+  bool use_tc = false;
+  CUtensorMap tmAct[2], tmD;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -114,15 +129,20 @@ static int make_geom(int ndim, int T, int H, int W, int C, int m1, int m2, int m
   return 0;
 }
 
+// bufAD holds A = fwdW(act) and later D = invH(.); on the tensor-core path D is stored as hi|lo planes
+static size_t ad_elems(const Geom& g, int B) {
+  return std::max(g.a_elems(B), (size_t)B * g.Tp * g.Hp * 2 * g.K2p * g.Cp);
+}
 static size_t spectral_scratch_floats(const Geom& g, int B) {
-  return align_up(g.a_elems(B), 64) + align_up(g.b_elems(B), 64) + 2 * align_up(g.s_elems(B), 64);
+  return align_up(ad_elems(g, B), 64) + align_up(g.b_elems(B), 64) + 2 * align_up(g.s_elems(B), 64);
 }
 
 // The truncated-DFT spectral operator on a channels-last activation:
 //   act -> D   (everything of SpectralConv3d.forward except the last inverse-W stage,
 //               which the layer kernel fuses with the bypass conv)
 static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
-                        float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr) {
+                        float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr,
+                        bool tc_planes = false) {
   const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
   {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
     StageScope sc(tm, ST_FWD_W, st);
@@ -155,8 +175,15 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   }
   {
     StageScope sc(tm, ST_INV_H, st);
-    B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
-                       (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+    if (tc_planes) {
+      // D[row=(g,h)][hl][k=(ri,kw)][o]: m = h*2+ri -> h * (2*K2p*Cp) + ri * (m3*Cp); lo plane at +K2p*Cp
+      const long long plane = (long long)g.K2p * g.Cp;
+      B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
+                         (long long)g.Hp * 2 * plane, 2 * plane, (int)n_hw, B * g.Tp, st, 2, n_hw, plane));
+    } else {
+      B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
+                         (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+    }
   }
   return 0;
 }
@@ -299,14 +326,24 @@ int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
     set_error("bad impl selector");
     return B200FNO_EINVAL;
   }
-  if (impl == B200FNO_IMPL_TC) {
-    set_error("tensor-core layer kernels are not available for this shape (width %d)", p->d.width);
+  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p;
+  if (impl == B200FNO_IMPL_TC && !can_tc) {
+    set_error("tensor-core layer kernel needs width 64 and modes3 in {4,8,12,16}; got width %d, modes3 %d",
+              p->d.width, p->d.modes3);
     return B200FNO_EINVAL;
+  }
+  if (p->ws) {
+    set_error("b200fno_plan_set_impl must be called before b200fno_plan_bind");
+    return B200FNO_ESTATE;
   }
   p->impl_request = impl;
   return 0;
 }
-int b200fno_plan_get_impl(const b200fno_plan_t* p) { return p ? B200FNO_IMPL_SIMT : B200FNO_EINVAL; }
+int b200fno_plan_get_impl(const b200fno_plan_t* p) {
+  if (!p) return B200FNO_EINVAL;
+  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p;
+  return (p->impl_request != B200FNO_IMPL_SIMT && can_tc) ? B200FNO_IMPL_TC : B200FNO_IMPL_SIMT;
+}
 
 size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* p) {
   if (!p) return 0;
@@ -318,7 +355,7 @@ static size_t packed_floats(const b200fno_plan* p) {
   const Geom& g = p->g;
   size_t n = align_up((size_t)p->Klp * g.Cp, 64);
   n += (size_t)p->d.n_layers *
-       (align_up((size_t)g.Cp * g.Cp, 64) + 2 * align_up(g.Cp, 64) + align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64));
+       (3 * align_up((size_t)g.Cp * g.Cp, 64) + 2 * align_up(g.Cp, 64) + align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64));
   n += align_up((size_t)g.Cp * 128, 64) + 128 + align_up((size_t)128 * p->Fp, 64) + align_up(p->Fp, 64);
   return n;
 }
@@ -344,7 +381,7 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   p->ws = w, p->ws_bytes = workspace_bytes;
   p->act[0] = w, w += align_up(g.act_elems(B), 64);
   p->act[1] = w, w += align_up(g.act_elems(B), 64);
-  p->bufAD = w, w += align_up(g.a_elems(B), 64);
+  p->bufAD = w, w += align_up(ad_elems(g, B), 64);
   p->bufBC = w, w += align_up(g.b_elems(B), 64);
   p->bufS = w, w += align_up(g.s_elems(B), 64);
   p->bufO = w;
@@ -357,12 +394,21 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     L.scale = q, q += align_up(g.Cp, 64);
     L.shift = q, q += align_up(g.Cp, 64);
     L.spec = q, q += align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64);
+    L.convHL = q, q += 2 * align_up((size_t)g.Cp * g.Cp, 64);
   }
   p->fc1T = q, q += align_up((size_t)g.Cp * 128, 64);
   p->fc1b = q, q += 128;
   p->fc2T = q, q += align_up((size_t)128 * p->Fp, 64);
   p->fc2b = q;
   p->weights_ready = false;
+  p->use_tc = p->impl_request != B200FNO_IMPL_SIMT && tc_layer_supported(g) && g.K2 == g.K2p;
+  if (p->use_tc) {
+    const long long rows = (long long)B * g.Tp * g.Hp;
+    B2_TRY(tc_make_act_map(&p->tmAct[0], p->act[0], rows, g));
+    B2_TRY(tc_make_act_map(&p->tmAct[1], p->act[1], rows, g));
+    B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
+    for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
+  }
   return 0;
 }
 
@@ -383,6 +429,8 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   for (int l = 0; l < p->d.n_layers; ++l) {
     LayerPacked& L = p->layers[l];
     B2_TRY(launch_transpose_pad(w->conv_w[l], C, C, L.convT, g.Cp, g.Cp, st));
+    if (g.Cp == C)  // tensor-core operand planes (K-major = the reference [o][i] layout)
+      B2_TRY(launch_split_hl(w->conv_w[l], C * C, L.convHL, L.convHL + align_up((size_t)g.Cp * g.Cp, 64), st));
     B2_TRY(launch_fold_bn(w->conv_b[l], w->bn_weight[l], w->bn_bias[l], w->bn_mean[l], w->bn_var[l], p->d.bn_eps, C,
                           g.Cp, L.scale, L.shift, st));
     B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, L.spec, g, C, C, p->d.modes1,
@@ -415,11 +463,16 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   const long long rows = (long long)B * g.Tp * g.Hp;
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerPacked& L = p->layers[l];
-    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing));
+    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing,
+                        p->use_tc));
     {
       StageScope sc(&p->timing, ST_LAYER, st);
-      B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows, g.Wp,
-                          g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
+      if (p->use_tc)
+        B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], L.tmW, p->tmD, p->tab.Gt, L.scale, L.shift, rows, g,
+                               l < d.n_layers - 1, st));
+      else
+        B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows,
+                            g.Wp, g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
     }
     cur ^= 1;
   }
@@ -544,7 +597,7 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
   float* a1 = ws;
   ws += align_up(g.act_elems(batch), 64);
   float* bufAD = ws;
-  ws += align_up(g.a_elems(batch), 64);
+  ws += align_up(ad_elems(g, batch), 64);
   float* bufBC = ws;
   ws += align_up(g.b_elems(batch), 64);
   float* bufS = ws;

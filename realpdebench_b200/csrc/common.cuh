@@ -85,7 +85,8 @@ void free_tables(Tables* t);
 // ---- SIMT stage launchers (simt.cu) ------------------------------------------
 // Out[g][m][n] = sum_k L[m][k] * R[g][k][n]   (n contiguous; N % 4 == 0)
 int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long strideRg, long long strideRk,
-                float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st);
+                float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st, int mdiv = 1,
+                long long strideOmLo = 0, long long split_off = 0);
 // O[b][ri][mode][o] = sum_i S[b][.][mode][i] (x) W[mode][i][.][o]   (complex)
 int launch_modes(const float* S, const float* Wpk, float* O, int B, int NM, int Cp, cudaStream_t st);
 // out[row][w][o] = f( (sum_i in[row][w][i] convT[i][o] + sum_k Gt[w][k] D[row][k][o]) * scale[o] + shift[o] )
@@ -129,5 +130,6 @@ int launch_transpose_pad(const float* src, int rows, int cols, float* dst, int d
 int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v,
                    float eps, int C, int Cp, float* scale, float* shift, cudaStream_t st);
 int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st);
+int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st);  // 3xTF32 planes
 
 }  // namespace b200fno

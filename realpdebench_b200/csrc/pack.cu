@@ -112,4 +112,18 @@ int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st
   return 0;
 }
 
+__global__ void split_hl_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float x = src[i], h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = x - h;
+  }
+}
+int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st) {
+  split_hl_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, n, dst_hi, dst_lo);
+  B2_LAUNCHED("split_hl_kernel");
+  return 0;
+}
+
 }  // namespace b200fno

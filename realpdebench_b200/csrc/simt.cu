@@ -61,7 +61,8 @@ template <int TM>
 __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ L, int ldl, int M, int K,
                                                       const float* __restrict__ R, long long strideRg,
                                                       long long strideRk, float* __restrict__ Out,
-                                                      long long strideOg, long long strideOm, int N) {
+                                                      long long strideOg, long long strideOm, int N, int mdiv,
+                                                      long long strideOmLo, long long split_off) {
   constexpr int NT = TM * 4;
   constexpr int A4 = TM * KC / 4 / NT;  // float4 per thread for the A tile (= 2)
   constexpr int B4 = KC * TN / 4 / NT;  // for the B tile (2 or 4)
@@ -113,22 +114,37 @@ __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       int m = m0 + ty * 4 + r;
-      if (m < M)
-        *reinterpret_cast<float4*>(Og + (long long)m * strideOm + n) =
-            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (m < M) {
+        // output row address: (m / mdiv) * strideOm + (m % mdiv) * strideOmLo  (mdiv == 1: plain m * strideOm)
+        float* dst = Og + (long long)(m / mdiv) * strideOm + (long long)(m % mdiv) * strideOmLo + n;
+        float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (split_off) {  // 3xTF32 operand planes for the tensor-core layer kernel: hi | lo
+          float4 hi = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
+                                  __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                  __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u),
+                                  __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          *reinterpret_cast<float4*>(dst) = hi;
+          *reinterpret_cast<float4*>(dst + split_off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        } else {
+          *reinterpret_cast<float4*>(dst) = v;
+        }
+      }
     }
   }
 }
 
 int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long strideRg, long long strideRk,
-                float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st) {
+                float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st, int mdiv,
+                long long strideOmLo, long long split_off) {
   if (G <= 0 || M <= 0) return 0;
   if (M <= 32) {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 32));
-    lmul_kernel<32><<<grid, 128, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N);
+    lmul_kernel<32><<<grid, 128, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
+                                          strideOmLo, split_off);
   } else {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 64));
-    lmul_kernel<64><<<grid, 256, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N);
+    lmul_kernel<64><<<grid, 256, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
+                                          strideOmLo, split_off);
   }
   B2_LAUNCHED("lmul_kernel");
   return 0;

@@ -1,0 +1,297 @@
+// Fused Fourier-layer body on the 5th-generation tensor cores (width 64):
+//
+//   out[p][o] = act( ( sum_i x[p][i] Wc[o][i]  +  sum_k G[w(p)][k] D[row][k][o] ) * scale[o] + shift[o] )
+//               \_____ bypass 1x1 conv ______/   \____ inverse-W DFT of the mixed modes ____/
+//
+// (fno.py:114-119: x1 + x2 -> BatchNorm (eval) -> GELU).  One CTA per SM, persistent over the tiles
+// (row, j) of its fixed W-tile index j; a tile is PT <= 128 consecutive points of one (b,t,h) row.
+//
+//   warp 0     TMA producer: x tile (2 boxes of 32 channels) into a 3-stage ring, D[row] (hi|lo planes)
+//   warp 1     MMA issuer: tcgen05.mma kind::tf32, A from TMEM (.ts form), B from shared memory
+//   warp 2     TMEM allocation (512 columns)
+//   warps 4-7  split: x tile smem -> registers -> TMEM as the A operand, hi = raw fp32 (the MMA truncates
+//              to tf32, measured in tests/test_gpu_tc_primitives.py) and lo = x - trunc(x)      [3xTF32]
+//   warps 8-11 epilogue: TMEM -> registers -> affine + GELU -> swizzled staging tile -> TMA store
+//
+// TMEM columns: [0,128) two accumulators, [128,384) two (x_hi | x_lo) A buffers, [384,512) G_hi | G_lo
+// (the inverse-W table rows of this CTA's W tile, loaded once).  Shared memory: 3 x 32 KB x ring,
+// 2 x 32 KB output staging, 32 KB conv weights (hi|lo, K-major), 2 x 16 KB D stages (MN-major).
+// fp32 parity: a*b = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation in TMEM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200fno {
+using namespace tc;
+
+constexpr int TCL_THREADS = 384;
+constexpr int NSX = 3;
+constexpr int XS_BYTES = 32768;   // x stage: 2 sub-tiles (32 ch) x 128 rows x 128 B
+constexpr int OS_BYTES = 32768;   // output staging buffer
+constexpr int W_BYTES = 32768;    // conv weights hi | lo, each 2 sub-tiles x 64 rows x 128 B
+constexpr int DS_BYTES = 16384;   // D stage: 2 N-blocks x (2*K2p <= 64) k-rows x 128 B
+constexpr int TCL_SMEM = NSX * XS_BYTES + 2 * OS_BYTES + W_BYTES + 2 * DS_BYTES + 1024;
+
+struct TcLayerArgs {
+  const float* Gt;  // [Wp][K2p] inverse-W table (scaled), fp32
+  const float *scale, *shift;
+  int rows, Wp, PT, NTW, G, K2p, gelu;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(TCL_THREADS, 1)
+    tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;
+  uint8_t* sOut = sX + NSX * XS_BYTES;
+  uint8_t* sW = sOut + 2 * OS_BYTES;
+  uint8_t* sD = sW + W_BYTES;
+  __shared__ uint64_t x_full[NSX], x_empty[NSX], d_full[2], d_empty[2], a_full[2], a_empty[2], acc_full[2],
+      acc_empty[2], w_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_scale[64], s_shift[64];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = blockIdx.x % a.NTW, g = blockIdx.x / a.NTW;
+  const int n_my = g < a.rows ? (a.rows - g + a.G - 1) / a.G : 0;
+  const int PT = a.PT, K2p = a.K2p;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1), mbar_init(&d_empty[i], 1);
+      mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
+    }
+    mbar_init(&w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  if (tid < 64) s_scale[tid] = a.scale[tid], s_shift[tid] = a.shift[tid];
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmX), prefetch_tensormap(&tmOut), prefetch_tensormap(&tmW), prefetch_tensormap(&tmD);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t T_ACC = tmem, T_A = tmem + 128, T_GHI = tmem + 384, T_GLO = tmem + 448;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_full, W_BYTES);
+      for (int hl = 0; hl < 2; ++hl)
+        for (int s = 0; s < 2; ++s) tma_load_2d(sW + hl * 16384 + s * 8192, &tmW, &w_full, 32 * s, 64 * hl);
+      for (int it = 0; it < n_my; ++it) {
+        const int row = g + it * a.G;
+        const int sx = it % NSX, px = (it / NSX) & 1;
+        mbar_wait(&x_empty[sx], px ^ 1);
+        mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
+        tma_load_3d(sX + sx * XS_BYTES, &tmX, &x_full[sx], 0, PT * j, row);
+        tma_load_3d(sX + sx * XS_BYTES + 16384, &tmX, &x_full[sx], 32, PT * j, row);
+        const int sd = it & 1, pd = (it >> 1) & 1;
+        mbar_wait(&d_empty[sd], pd ^ 1);
+        mbar_arrive_expect_tx(&d_full[sd], (uint32_t)(2 * 2 * K2p * 128));
+        tma_load_2d(sD + sd * DS_BYTES, &tmD, &d_full[sd], 0, row * 2 * K2p);
+        tma_load_2d(sD + sd * DS_BYTES + 2 * K2p * 128, &tmD, &d_full[sd], 32, row * 2 * K2p);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_w = make_idesc_tf32(128, 64, 0, 0), idesc_d = make_idesc_tf32(128, 64, 0, 1);
+      const uint32_t w_addr = smem_u32(sW), d_addr = smem_u32(sD);
+      const int nk2 = K2p / 8;
+      mbar_wait(&w_full, 0);
+      for (int it = 0; it < n_my; ++it) {
+        const int t = it & 1, pt = (it >> 1) & 1;
+        mbar_wait(&a_full[t], pt);
+        mbar_wait(&d_full[t], pt);
+        mbar_wait(&acc_empty[t], pt ^ 1);
+        tc_fence_after();
+        const uint32_t acc = T_ACC + t * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
+        const uint32_t dbase = d_addr + t * DS_BYTES;
+        auto descW = [&](int hl, int ks) {
+          return make_smem_desc(w_addr + hl * 16384 + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
+        };
+        auto descD = [&](int hl, int ks) {
+          return make_smem_desc(dbase + (hl * K2p + ks * 8) * 128, 2 * K2p * 128, 512, LAYOUT_SW128_BASE32B);
+        };
+        uint32_t accum = 0;
+        // small (lo) terms first, then the hi*hi terms
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Alo + ks * 8, descW(0, ks), idesc_w, accum), accum = 1;
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Ahi + ks * 8, descW(1, ks), idesc_w, 1);
+        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GLO + ks * 8, descD(0, ks), idesc_d, 1);
+        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GHI + ks * 8, descD(1, ks), idesc_d, 1);
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Ahi + ks * 8, descW(0, ks), idesc_w, 1);
+        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GHI + ks * 8, descD(0, ks), idesc_d, 1);
+        umma_commit(&a_empty[t]);
+        umma_commit(&d_empty[t]);
+        umma_commit(&acc_full[t]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ split warps (A operand producers)
+    const int q = warp - 4, p = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // inverse-W table rows of this W tile -> TMEM, once
+      const int w = PT * j + p;
+      const bool valid = p < PT && w < a.Wp;
+      for (int k0 = 0; k0 < K2p; k0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = valid ? __ldg(a.Gt + (size_t)w * K2p + k0 + i) : 0.f;
+          hi[i] = __float_as_uint(x);
+          lo[i] = __float_as_uint(x - tf32_hi(x));
+        }
+        tmem_st8(T_GHI + lane_addr + k0, hi);
+        tmem_st8(T_GLO + lane_addr + k0, lo);
+      }
+    }
+    for (int it = 0; it < n_my; ++it) {
+      const int sx = it % NSX, px = (it / NSX) & 1, t = it & 1, pt = (it >> 1) & 1;
+      mbar_wait(&x_full[sx], px);
+      mbar_wait(&a_empty[t], pt ^ 1);
+      tc_fence_after();
+      const uint32_t Ahi = T_A + t * 128 + lane_addr, Alo = Ahi + 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        const uint8_t* base = sX + sx * XS_BYTES + half * 16384;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 u = *reinterpret_cast<const uint4*>(base + sw128_off(p, c));
+          v[4 * c] = u.x, v[4 * c + 1] = u.y, v[4 * c + 2] = u.z, v[4 * c + 3] = u.w;
+        }
+        if (p >= PT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        tmem_st32(Ahi + half * 32, v);
+        if (half == 1) {  // every shared-memory read of this stage has been consumed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_empty[sx]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]);
+          v[i] = __float_as_uint(x - tf32_hi(x));
+        }
+        tmem_st32(Alo + half * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&a_full[t]);
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp - 8, p = q * 32 + lane, etid = tid - 256;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < n_my; ++it) {
+      const int row = g + it * a.G, t = it & 1, pt = (it >> 1) & 1, buf = it & 1;
+      mbar_wait(&acc_full[t], pt);
+      tc_fence_after();
+      if (etid == 0) tma_store_wait_read<1>();  // the store that last used staging[buf] has read it
+      named_bar_sync(1, 128);
+      uint8_t* stage = sOut + buf * OS_BYTES;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(T_ACC + t * 64 + lane_addr + half * 32, v);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[t]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + half * 32 + 4 * c);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + half * 32 + 4 * c);
+          float4 y = make_float4(fmaf(__uint_as_float(v[4 * c]), sc.x, sh.x), fmaf(__uint_as_float(v[4 * c + 1]), sc.y, sh.y),
+                                 fmaf(__uint_as_float(v[4 * c + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[4 * c + 3]), sc.w, sh.w));
+          if (a.gelu) y = make_float4(gelu_erf_tc(y.x), gelu_erf_tc(y.y), gelu_erf_tc(y.z), gelu_erf_tc(y.w));
+          *reinterpret_cast<float4*>(stage + half * 16384 + sw128_off(p, c)) = y;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (etid == 0) {
+        tma_store_3d(&tmOut, stage, 0, PT * j, row);
+        tma_store_3d(&tmOut, stage + 16384, 32, PT * j, row);
+        tma_store_commit();
+      }
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+bool tc_layer_supported(const Geom& g) {
+  return g.Cp == 64 && g.K2p % 8 == 0 && g.K2p <= 32 && ceil_div(g.Wp, 128) <= 148;
+}
+
+int tc_layer_tile(const Geom& g, int* PT, int* NTW) {
+  *NTW = ceil_div(g.Wp, 128);
+  *PT = round_up(ceil_div(g.Wp, *NTW), 8);
+  return 0;
+}
+
+// tensor maps over channels-last activations [rows][Wp][64]: box = 32 channels x PT points
+int tc_make_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g) {
+  int PT, NTW;
+  tc_layer_tile(g, &PT, &NTW);
+  uint64_t dims[3] = {64, (uint64_t)g.Wp, (uint64_t)rows};
+  uint64_t strides[2] = {64 * 4, (uint64_t)g.Wp * 64 * 4};
+  uint32_t box[3] = {32, (uint32_t)PT, 1};
+  return encode_tensor_map(m, act, 3, dims, strides, box, 1);
+}
+// conv weights hi|lo: [2*64 rows (hl, o)][64 i], K-major boxes of 32 i x 64 o
+int tc_make_w_map(CUtensorMap* m, const float* w_hl) {
+  uint64_t dims[2] = {64, 128};
+  uint64_t strides[1] = {64 * 4};
+  uint32_t box[2] = {32, 64};
+  return encode_tensor_map(m, w_hl, 2, dims, strides, box, 1);
+}
+// D planes: [rows * 2 * K2p k-rows][64 o], MN-major boxes of 32 o x 2*K2p k-rows, 32-byte swizzle atoms
+int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g) {
+  uint64_t dims[2] = {64, (uint64_t)rows * 2 * g.K2p};
+  uint64_t strides[1] = {64 * 4};
+  uint32_t box[2] = {32, (uint32_t)(2 * g.K2p)};
+  return encode_tensor_map(m, d, 2, dims, strides, box, 2);
+}
+
+int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
+                    const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
+                    cudaStream_t st) {
+  TcLayerArgs a{};
+  tc_layer_tile(g, &a.PT, &a.NTW);
+  a.Gt = Gt, a.scale = scale, a.shift = shift;
+  a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
+  a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
+  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
+  tc_layer_kernel<<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
+  B2_LAUNCHED("tc_layer_kernel");
+  return 0;
+}
+
+}  // namespace b200fno

@@ -160,6 +160,10 @@ class FNOEngine:
                                               stream))
         return out
 
+    def resolved_impl(self) -> str:
+        """'tc' if the tcgen05 layer kernel is in use for this shape, else 'simt' (plan must exist)."""
+        return "tc" if _capi.lib().b200fno_plan_get_impl(self._plan) == _capi.IMPL_TC else "simt"
+
     def timing(self, on: bool) -> None:
         """Bracket every stage launch with CUDA events (bench.py's per-kernel roofline numbers)."""
         check(_capi.lib().b200fno_timing_enable(self._plan, int(on)))

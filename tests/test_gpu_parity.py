@@ -160,6 +160,40 @@ def test_fno2d_bench_shape_batch_consistency(R):
     assert torch.equal(m(x[1:].to(dev())), y[1:])
 
 
+# ---------------------------------------------------------------- tensor-core layer kernel
+@pytest.mark.parametrize("ndim,modes,s", [
+    (2, (6, 8), (3, 40, 150, 3)),       # W' = 156 -> two W tiles of 80 points
+    (2, (12, 16), (2, 20, 250, 2)),     # W' = 256 -> two full 128-point tiles
+    (3, (2, 4, 16), (4, 10, 60, 2)),    # 3-D rows (b,t,h), single 72-point tile
+    (2, (5, 4), (2, 9, 700, 1)),        # six W tiles, odd H'
+])
+def test_tc_layer_kernel_matches_oracle_and_simt(R, ndim, modes, s):
+    torch.manual_seed(12)
+    sd = O.init_state(ndim, modes, 3, 64, s, s)
+    O.randomize_bn(sd, 3)
+    mk = (lambda: R.FNO3d(*modes, 3, 64, s, s)) if ndim == 3 else (lambda: R.FNO2d(*modes, 3, 64, s, s))
+    x = torch.randn(5, *s)
+    ref = (O.fno3d_forward if ndim == 3 else O.fno2d_forward)(sd, x, s)
+    outs = {}
+    for impl in ("tc", "simt"):
+        m = mk()
+        m.load_state_dict(sd)
+        m = m.to(dev()).eval()
+        m.set_impl(impl)
+        outs[impl] = m(x.to(dev())).cpu()
+        assert m.engine.resolved_impl() == impl
+        assert O.rel_l2(outs[impl], ref) < TOL, impl
+    assert O.rel_l2(outs["tc"], outs["simt"]) < TOL
+
+
+def test_tc_rejected_for_unsupported_width(R, golden):
+    g = golden("kat_a.pt")  # width 8
+    m = make3d(R, g["ctor"], g["sd"])
+    m.set_impl("tc")
+    with pytest.raises(RuntimeError, match="width 64"):
+        m(g["x"].to(dev()))
+
+
 # ---------------------------------------------------------------- rollout
 @pytest.mark.parametrize("case", ["plain", "controlled", "range"])
 def test_rollout_golden(R, golden, case):
