@@ -15,6 +15,15 @@ bool tc_layer_supported(const Geom& g);
 int tc_make_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g);
 int tc_make_w_map(CUtensorMap* m, const float* w_hl);
 int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g);
+bool tc_proj_supported(const Geom& g, int Fout);
+int tc_proj_n2(int Fout);
+int tc_make_proj_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g, int W);
+int tc_make_fc1_map(CUtensorMap* m, const float* w);
+int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2);
+int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+                   cudaStream_t st);
+int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
+                   cudaStream_t st);
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
                     const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
                     cudaStream_t st);
@@ -103,8 +112,12 @@ struct b200fno_plan {
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
   std::vector<LayerPacked> layers;
   // tensor-core path
-  bool use_tc = false;
-  CUtensorMap tmAct[2], tmD;
+  bool use_tc = false, use_tc_lift = false;
+  CUtensorMap tmAct[2], tmD, tmW0;
+  float* W0K = nullptr;  // [2][64][64] lift weights as K-major hi|lo planes
+  bool use_tc_proj = false;
+  CUtensorMap tmActProj[2], tmFc1, tmFc2;
+  float *fc1HL = nullptr, *fc2HL = nullptr;  // [2][128][64], [2][N2][128]
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -353,7 +366,7 @@ size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* p) {
 
 static size_t packed_floats(const b200fno_plan* p) {
   const Geom& g = p->g;
-  size_t n = align_up((size_t)p->Klp * g.Cp, 64);
+  size_t n = align_up((size_t)p->Klp * g.Cp, 64) + 2 * 4096 + 2 * 128 * 64 + 2 * 64 * 128;
   n += (size_t)p->d.n_layers *
        (3 * align_up((size_t)g.Cp * g.Cp, 64) + 2 * align_up(g.Cp, 64) + align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64));
   n += align_up((size_t)g.Cp * 128, 64) + 128 + align_up((size_t)128 * p->Fp, 64) + align_up(p->Fp, 64);
@@ -388,6 +401,9 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   float* q = (float*)packed;
   p->packed = q, p->packed_bytes = packed_bytes;
   p->W0T = q, q += align_up((size_t)p->Klp * g.Cp, 64);
+  p->W0K = q, q += 2 * 4096;
+  p->fc1HL = q, q += 2 * 128 * 64;
+  p->fc2HL = q, q += 2 * 64 * 128;
   p->layers.resize(p->d.n_layers);
   for (auto& L : p->layers) {
     L.convT = q, q += align_up((size_t)g.Cp * g.Cp, 64);
@@ -408,6 +424,15 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     B2_TRY(tc_make_act_map(&p->tmAct[1], p->act[1], rows, g));
     B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
+    p->use_tc_lift = round_up(p->Klp, 8) <= 64;
+    if (p->use_tc_lift) B2_TRY(tc_make_w_map(&p->tmW0, p->W0K));
+    p->use_tc_proj = tc_proj_supported(g, p->Fout);
+    if (p->use_tc_proj) {
+      B2_TRY(tc_make_proj_act_map(&p->tmActProj[0], p->act[0], rows, g, p->d.w));
+      B2_TRY(tc_make_proj_act_map(&p->tmActProj[1], p->act[1], rows, g, p->d.w));
+      B2_TRY(tc_make_fc1_map(&p->tmFc1, p->fc1HL));
+      B2_TRY(tc_make_fc2_map(&p->tmFc2, p->fc2HL, tc_proj_n2(p->Fout)));
+    }
   }
   return 0;
 }
@@ -426,6 +451,10 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   const int C = p->d.width, nf = p->Fin + p->ng;
   B2_TRY(launch_transpose_pad(w->fc0_w, C, nf, p->W0T, p->Klp, g.Cp, st));
   B2_TRY(launch_pad_copy(w->fc0_b, C, p->W0T + (size_t)nf * g.Cp, g.Cp, st));
+  if (p->use_tc_lift) {  // W0K[c][k] = W0T[k][c] (bias row included), then split in place into hi | lo
+    B2_TRY(launch_transpose_pad(p->W0T, p->Klp, g.Cp, p->W0K, 64, 64, st));
+    B2_TRY(launch_split_hl(p->W0K, 4096, p->W0K, p->W0K + 4096, st));
+  }
   for (int l = 0; l < p->d.n_layers; ++l) {
     LayerPacked& L = p->layers[l];
     B2_TRY(launch_transpose_pad(w->conv_w[l], C, C, L.convT, g.Cp, g.Cp, st));
@@ -440,6 +469,12 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   B2_TRY(launch_pad_copy(w->fc1_b, 128, p->fc1b, 128, st));
   B2_TRY(launch_transpose_pad(w->fc2_w, p->Fout, 128, p->fc2T, 128, p->Fp, st));
   B2_TRY(launch_pad_copy(w->fc2_b, p->Fout, p->fc2b, p->Fp, st));
+  if (p->use_tc_proj) {  // K-major (= reference [out][in]) hi | lo planes for the tensor-core projection
+    const int N2 = tc_proj_n2(p->Fout);
+    B2_TRY(launch_split_hl(w->fc1_w, 128 * 64, p->fc1HL, p->fc1HL + 128 * 64, st));
+    B2_TRY(launch_pad_copy(w->fc2_w, p->Fout * 128, p->fc2HL, N2 * 128, st));
+    B2_TRY(launch_split_hl(p->fc2HL, N2 * 128, p->fc2HL, p->fc2HL + N2 * 128, st));
+  }
   p->weights_ready = true;
   return 0;
 }
@@ -457,7 +492,12 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   la.x_sT = d.ndim == 3 ? (long long)d.h * d.w * d.c_in : 0;
   {
     StageScope sc(&p->timing, ST_LIFT, st);
-    B2_TRY(launch_lift(la, st));
+    if (p->use_tc_lift) {
+      la.Klp = round_up(p->Klp, 8);
+      B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st));
+    } else {
+      B2_TRY(launch_lift(la, st));
+    }
   }
   int cur = 0;
   const long long rows = (long long)B * g.Tp * g.Hp;
@@ -496,6 +536,7 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a
   pa.st_sB = (long long)d.t_in * HW * d.c_in;
   pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
   StageScope sc(&p->timing, ST_PROJ, st);
+  if (p->use_tc_proj) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
   return launch_proj(pa, st);
 }
 

@@ -24,21 +24,45 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware (no issue slots burnt) until the phase
+// completes or the hint expires, instead of spinning on the barrier.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)  // suspend-time hint, ns
       : "memory");
   return ok != 0;
 }
-// Bounded wait: try_wait suspends for a HW-defined window per call; ~2^22 calls is far beyond any
-// legitimate wait in these kernels.  On expiry the kernel traps (launch fails, the box stays healthy).
+// Bounded wait: far beyond any legitimate wait in these kernels; on expiry the kernel traps
+// (the launch fails, the box stays healthy) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 22); ++i)
+  uint64_t t0 = 0;
+#pragma unroll 1
+  for (uint32_t i = 0;; ++i) {
     if (mbar_try_wait(bar, parity)) return;
-  __trap();
+    if ((i & 63u) == 63u) {  // wall-clock bound: 2 s without progress is a deadlock, not a wait
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+// explicit shared-state-space vector accesses (keeps ptxas from falling back to generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------

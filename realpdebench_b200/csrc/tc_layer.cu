@@ -11,7 +11,8 @@
 //   warp 2     TMEM allocation (512 columns)
 //   warps 4-7  split: x tile smem -> registers -> TMEM as the A operand, hi = raw fp32 (the MMA truncates
 //              to tf32, measured in tests/test_gpu_tc_primitives.py) and lo = x - trunc(x)      [3xTF32]
-//   warps 8-11 epilogue: TMEM -> registers -> affine + GELU -> swizzled staging tile -> TMA store
+//   warps 8-15 epilogue: TMEM -> registers -> affine + GELU -> swizzled staging tile -> TMA store
+//              (warp w: TMEM lane quarter w%4, channel half (w-8)/4)
 //
 // TMEM columns: [0,128) two accumulators, [128,384) two (x_hi | x_lo) A buffers, [384,512) G_hi | G_lo
 // (the inverse-W table rows of this CTA's W tile, loaded once).  Shared memory: 3 x 32 KB x ring,
@@ -23,7 +24,8 @@
 namespace b200fno {
 using namespace tc;
 
-constexpr int TCL_THREADS = 384;
+constexpr int TCL_THREADS = 512;
+constexpr int EPI_THREADS = 256;
 constexpr int NSX = 3;
 constexpr int XS_BYTES = 32768;   // x stage: 2 sub-tiles (32 ch) x 128 rows x 128 B
 constexpr int OS_BYTES = 32768;   // output staging buffer
@@ -31,10 +33,18 @@ constexpr int W_BYTES = 32768;    // conv weights hi | lo, each 2 sub-tiles x 64
 constexpr int DS_BYTES = 16384;   // D stage: 2 N-blocks x (2*K2p <= 64) k-rows x 128 B
 constexpr int TCL_SMEM = NSX * XS_BYTES + 2 * OS_BYTES + W_BYTES + 2 * DS_BYTES + 1024;
 
+enum { MODE_LAYER = 0, MODE_LIFT = 1 };
+
 struct TcLayerArgs {
   const float* Gt;  // [Wp][K2p] inverse-W table (scaled), fp32
   const float *scale, *shift;
   int rows, Wp, PT, NTW, G, K2p, gelu;
+  // MODE_LIFT only (fno.py:106-111): A tile = [input features | grid coordinates | 1] built from x
+  const float* x;
+  const int* in_off;
+  const float *gt, *gh, *gw;
+  int Tv, H, W, Tp, Hp, c_in, Fin, ng, nkl;  // nkl = K steps (Klp / 8)
+  long long x_sB, x_sT;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -50,8 +60,22 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
-__device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// GELU (erf form, F.gelu default) without branches: v*Phi(v) = max(v,0) - |v| * 0.5*erfc(|v|/sqrt2), with
+// erfc from Abramowitz-Stegun 7.1.26 (|eps| <= 1.5e-7).  Max abs error vs the exact function 5.3e-7 over
+// [-12,12] (torch's own fp32 gelu: 1.2e-6), relative L2 9e-8 on N(0,1) inputs; 15 instructions, 2 MUFU.
+__device__ __forceinline__ float gelu_erf_tc(float v) {
+  const float av = fabsf(v);
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  poly *= t;
+  const float e = exp2f(v * v * (-0.5f * 1.4426950408889634f));
+  return fmaxf(v, 0.0f) - av * poly * e;
+}
 
+template <int MODE>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
@@ -65,6 +89,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       acc_empty[2], w_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[64], s_shift[64];
+  __shared__ int s_inoff[64];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = blockIdx.x % a.NTW, g = blockIdx.x / a.NTW;
@@ -76,13 +101,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1), mbar_init(&d_empty[i], 1);
       mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
-      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], EPI_THREADS);
     }
     mbar_init(&w_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
-  if (tid < 64) s_scale[tid] = a.scale[tid], s_shift[tid] = a.shift[tid];
+  if (tid < 64) s_scale[tid] = a.scale ? a.scale[tid] : 1.f, s_shift[tid] = a.shift ? a.shift[tid] : 0.f;
+  if (MODE == MODE_LIFT && tid < 64) s_inoff[tid] = tid < a.Fin ? a.in_off[tid] : 0;
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX), prefetch_tensormap(&tmOut), prefetch_tensormap(&tmW), prefetch_tensormap(&tmD);
   }
@@ -98,7 +124,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       mbar_arrive_expect_tx(&w_full, W_BYTES);
       for (int hl = 0; hl < 2; ++hl)
         for (int s = 0; s < 2; ++s) tma_load_2d(sW + hl * 16384 + s * 8192, &tmW, &w_full, 32 * s, 64 * hl);
-      for (int it = 0; it < n_my; ++it) {
+      for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
         const int row = g + it * a.G;
         const int sx = it % NSX, px = (it / NSX) & 1;
         mbar_wait(&x_empty[sx], px ^ 1);
@@ -122,10 +148,22 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       for (int it = 0; it < n_my; ++it) {
         const int t = it & 1, pt = (it >> 1) & 1;
         mbar_wait(&a_full[t], pt);
-        mbar_wait(&d_full[t], pt);
+        if (MODE == MODE_LAYER) mbar_wait(&d_full[t], pt);
         mbar_wait(&acc_empty[t], pt ^ 1);
         tc_fence_after();
         const uint32_t acc = T_ACC + t * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
+        if (MODE == MODE_LIFT) {
+          for (int ks = 0; ks < a.nkl; ++ks) {
+            const uint64_t whi = make_smem_desc(w_addr + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
+            const uint64_t wlo = make_smem_desc(w_addr + 16384 + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
+            umma_tf32_ts(acc, Alo + ks * 8, whi, idesc_w, ks > 0);
+            umma_tf32_ts(acc, Ahi + ks * 8, wlo, idesc_w, 1);
+            umma_tf32_ts(acc, Ahi + ks * 8, whi, idesc_w, 1);
+          }
+          umma_commit(&a_empty[t]);
+          umma_commit(&acc_full[t]);
+          continue;
+        }
         const uint32_t dbase = d_addr + t * DS_BYTES;
         auto descW = [&](int hl, int ks) {
           return make_smem_desc(w_addr + hl * 16384 + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
@@ -150,7 +188,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     // ------------------------------------------------------------------ split warps (A operand producers)
     const int q = warp - 4, p = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    {  // inverse-W table rows of this W tile -> TMEM, once
+    if (MODE == MODE_LAYER) {  // inverse-W table rows of this W tile -> TMEM, once
       const int w = PT * j + p;
       const bool valid = p < PT && w < a.Wp;
       for (int k0 = 0; k0 < K2p; k0 += 8) {
@@ -165,7 +203,63 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
         tmem_st8(T_GLO + lane_addr + k0, lo);
       }
     }
-    for (int it = 0; it < n_my; ++it) {
+    if (MODE == MODE_LIFT && n_my > 0) {
+      // A row of point p = [input features gathered from x | grid coordinates | 1 (bias)].
+      // The gather for tile it+1 is issued before tile it is converted, so its latency overlaps the
+      // TMEM stores and the wait for the A buffer instead of being exposed once per tile.
+      uint32_t r[64];
+      bool valid = false;
+      int h = 0, tt = 0, w = 0;
+      auto gather = [&](int it) {
+        const int row = g + it * a.G;
+        h = row % a.Hp, tt = (row / a.Hp) % a.Tp;
+        const int b = row / (a.Hp * a.Tp);
+        w = PT * j + p;
+        valid = p < PT && w < a.W && h < a.H && tt < a.Tv;
+        const float* xp = a.x + (size_t)b * a.x_sB + (size_t)min(tt, a.Tv - 1) * a.x_sT +
+                          ((size_t)min(h, a.H - 1) * a.W + min(w, a.W - 1)) * a.c_in;
+#pragma unroll
+        for (int f = 0; f < 64; ++f)
+          if (f < a.Fin) r[f] = __float_as_uint(__ldg(xp + s_inoff[f]));
+      };
+      gather(0);
+      for (int it = 0; it < n_my; ++it) {
+        const int t = it & 1, pt = (it >> 1) & 1;
+        mbar_wait(&a_empty[t], pt ^ 1);
+        tc_fence_after();
+        const uint32_t Ahi = T_A + t * 128 + lane_addr, Alo = Ahi + 64;
+        const float gtv = a.gt ? __ldg(a.gt + min(tt, a.Tv - 1)) : 0.f, ghv = __ldg(a.gh + min(h, a.H - 1)),
+                    gwv = __ldg(a.gw + min(w, a.W - 1));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half * 32 >= a.nkl * 8) break;
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int f = half * 32 + i;
+            float x = 0.f;
+            if (f < a.Fin) x = __uint_as_float(r[f]);
+            else if (f < a.Fin + a.ng) {
+              const int gi = f - a.Fin + (a.gt ? 0 : 1);  // 0: t, 1: h, 2: w
+              x = gi == 0 ? gtv : (gi == 1 ? ghv : gwv);
+            } else if (f == a.Fin + a.ng) x = 1.f;
+            v[i] = valid ? __float_as_uint(x) : 0u;
+          }
+          tmem_st32(Ahi + half * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]);
+            v[i] = __float_as_uint(x - tf32_hi(x));
+          }
+          tmem_st32(Alo + half * 32, v);
+        }
+        if (it + 1 < n_my) gather(it + 1);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&a_full[t]);
+      }
+    }
+    for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
       const int sx = it % NSX, px = (it / NSX) & 1, t = it & 1, pt = (it >> 1) & 1;
       mbar_wait(&x_full[sx], px);
       mbar_wait(&a_empty[t], pt ^ 1);
@@ -174,10 +268,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        const uint8_t* base = sX + sx * XS_BYTES + half * 16384;
+        const uint32_t base = smem_u32(sX) + sx * XS_BYTES + half * 16384;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          uint4 u = *reinterpret_cast<const uint4*>(base + sw128_off(p, c));
+          uint4 u = lds128(base + sw128_off(p, c));
           v[4 * c] = u.x, v[4 * c + 1] = u.y, v[4 * c + 2] = u.z, v[4 * c + 3] = u.w;
         }
         if (p >= PT) {
@@ -202,39 +296,38 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp - 8, p = q * 32 + lane, etid = tid - 256;
+    const int q = warp & 3, half = (warp - 8) >> 2, p = q * 32 + lane, etid = tid - 256;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float sc[32], sh[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sc[i] = s_scale[half * 32 + i], sh[i] = s_shift[half * 32 + i];
     for (int it = 0; it < n_my; ++it) {
       const int row = g + it * a.G, t = it & 1, pt = (it >> 1) & 1, buf = it & 1;
       mbar_wait(&acc_full[t], pt);
       tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(T_ACC + t * 64 + lane_addr + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[t]);
       if (etid == 0) tma_store_wait_read<1>();  // the store that last used staging[buf] has read it
-      named_bar_sync(1, 128);
-      uint8_t* stage = sOut + buf * OS_BYTES;
+      named_bar_sync(1, EPI_THREADS);
+      const uint32_t stage = smem_u32(sOut) + buf * OS_BYTES + half * 16384;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(T_ACC + t * 64 + lane_addr + half * 32, v);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(&acc_empty[t]);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + half * 32 + 4 * c);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + half * 32 + 4 * c);
-          float4 y = make_float4(fmaf(__uint_as_float(v[4 * c]), sc.x, sh.x), fmaf(__uint_as_float(v[4 * c + 1]), sc.y, sh.y),
-                                 fmaf(__uint_as_float(v[4 * c + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[4 * c + 3]), sc.w, sh.w));
-          if (a.gelu) y = make_float4(gelu_erf_tc(y.x), gelu_erf_tc(y.y), gelu_erf_tc(y.z), gelu_erf_tc(y.w));
-          *reinterpret_cast<float4*>(stage + half * 16384 + sw128_off(p, c)) = y;
-        }
+      for (int c = 0; c < 8; ++c) {
+        float y0 = fmaf(__uint_as_float(v[4 * c]), sc[4 * c], sh[4 * c]);
+        float y1 = fmaf(__uint_as_float(v[4 * c + 1]), sc[4 * c + 1], sh[4 * c + 1]);
+        float y2 = fmaf(__uint_as_float(v[4 * c + 2]), sc[4 * c + 2], sh[4 * c + 2]);
+        float y3 = fmaf(__uint_as_float(v[4 * c + 3]), sc[4 * c + 3], sh[4 * c + 3]);
+        if (a.gelu) y0 = gelu_erf_tc(y0), y1 = gelu_erf_tc(y1), y2 = gelu_erf_tc(y2), y3 = gelu_erf_tc(y3);
+        sts128(stage + sw128_off(p, c), y0, y1, y2, y3);
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_THREADS);
       if (etid == 0) {
-        tma_store_3d(&tmOut, stage, 0, PT * j, row);
-        tma_store_3d(&tmOut, stage + 16384, 32, PT * j, row);
+        const uint8_t* st = sOut + buf * OS_BYTES;
+        tma_store_3d(&tmOut, st, 0, PT * j, row);
+        tma_store_3d(&tmOut, st + 16384, 32, PT * j, row);
         tma_store_commit();
       }
     }
@@ -288,9 +381,26 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.Gt = Gt, a.scale = scale, a.shift = shift;
   a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
-  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
-  tc_layer_kernel<<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
+  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
+  tc_layer_kernel<MODE_LAYER><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
   B2_LAUNCHED("tc_layer_kernel");
+  return 0;
+}
+
+// Lift on tensor cores: act0 = [x | grid | 1] * W0K^T, zero in the pad region.  W0K: [2 (hi|lo)][64 ch][64 k].
+int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
+                   cudaStream_t st) {
+  TcLayerArgs a{};
+  tc_layer_tile(g, &a.PT, &a.NTW);
+  a.rows = la.B * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;
+  a.G = std::max(1, std::min(148 / a.NTW, a.rows));
+  a.x = la.x, a.in_off = la.in_off, a.gt = la.gt, a.gh = la.gh, a.gw = la.gw;
+  a.Tv = la.T, a.H = la.H, a.W = la.W, a.Tp = g.Tp, a.Hp = g.Hp, a.c_in = la.c_in, a.Fin = la.Fin, a.ng = la.ng;
+  a.nkl = la.Klp / 8;
+  a.x_sB = la.x_sB, a.x_sT = la.x_sT;
+  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
+  tc_layer_kernel<MODE_LIFT><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmOut, tmOut, tmW0, tmW0);
+  B2_LAUNCHED("tc_lift_kernel");
   return 0;
 }
 

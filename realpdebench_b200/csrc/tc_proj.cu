@@ -1,0 +1,301 @@
+// Projection + rollout glue on the tensor cores (width 64):
+//
+//   crop -> fc1 (64 -> 128) -> GELU -> fc2 (128 -> F) -> unfold -> p*a[c] + b[c] -> prediction slice / next input
+//   (fno.py:121-128; eval.py:315-318 as one per-channel affine)
+//
+// Two chained 3xTF32 GEMMs per tile of PT <= 128 valid points; the hidden activations never leave
+// the SM: GEMM-1 accumulates in TMEM, the epilogue warps apply bias + GELU and write the result
+// straight back into TMEM as the (hi | lo) A operand of GEMM-2.
+//
+//   warp 0     TMA: fc1 / fc2 weights once (hi|lo, K-major), x tiles into a 3-stage ring
+//   warp 1     MMA issuer (A from TMEM, B from shared memory)
+//   warp 2     TMEM allocation
+//   warps 4-7  split: x tile -> TMEM (x_hi | x_lo)
+//   warps 8-15 epilogue 1 (bias, GELU, hi/lo -> TMEM) and epilogue 2 (bias, affine, scatter stores)
+//
+// TMEM columns: [0,128) x_hi|x_lo, [128,256) accumulator (GEMM-2 reuses it), [256,512) h_hi|h_lo.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200fno {
+using namespace tc;
+
+constexpr int TCP_THREADS = 512;
+constexpr int TCP_EPI = 256;
+constexpr int TCP_NSX = 3;
+constexpr int TCP_XS = 32768;
+constexpr int TCP_W1 = 65536;  // [hl][2 k-subtiles][128 rows][128 B]
+constexpr int TCP_W2 = 65536;  // [hl][4 k-subtiles][N2 <= 64 rows][128 B]
+constexpr int TCP_SMEM = TCP_NSX * TCP_XS + TCP_W1 + TCP_W2 + 1024;
+
+struct TcProjArgs {
+  const float *fc1b, *fc2b;      // [128], [>= Fout]
+  const float *aff_a, *aff_b;    // per physical channel or nullptr
+  const int *chan, *out_off, *st_off;
+  float *out, *state;
+  int rows, Tv, H, W, Tp, Hp, PT, NTW, G, Fout, N2, c_out, c_in;
+  long long out_sB, out_sT, st_sB, st_sT;
+};
+
+__device__ __forceinline__ void tcp_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tcp_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// same branch-free erf-GELU as tc_layer.cu (max abs error 5.3e-7)
+__device__ __forceinline__ float tcp_gelu(float v) {
+  const float av = fabsf(v);
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  poly *= t;
+  const float e = exp2f(v * v * (-0.5f * 1.4426950408889634f));
+  return fmaxf(v, 0.0f) - av * poly * e;
+}
+
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+    tc_proj_kernel(TcProjArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                   const __grid_constant__ CUtensorMap tmW2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;
+  uint8_t* sW1 = sX + TCP_NSX * TCP_XS;
+  uint8_t* sW2 = sW1 + TCP_W1;
+  __shared__ uint64_t x_full[TCP_NSX], x_empty[TCP_NSX], w_full, xa_full, xa_empty, acc1_full, h_full, acc2_full,
+      acc_free;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_b1[128], s_b2[64], s_fa[64], s_fb[64];
+  __shared__ int s_oo[64], s_so[64];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = blockIdx.x % a.NTW, g = blockIdx.x / a.NTW;
+  const int n_my = g < a.rows ? (a.rows - g + a.G - 1) / a.G : 0;
+  const int PT = a.PT, N2 = a.N2;
+
+  if (tid == 0) {
+    for (int i = 0; i < TCP_NSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
+    mbar_init(&w_full, 1);
+    mbar_init(&xa_full, 128), mbar_init(&xa_empty, 1);
+    mbar_init(&acc1_full, 1), mbar_init(&h_full, TCP_EPI);
+    mbar_init(&acc2_full, 1), mbar_init(&acc_free, TCP_EPI);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  if (tid < 128) s_b1[tid] = a.fc1b[tid];
+  if (tid < 64) {
+    const bool on = tid < a.Fout;
+    const int ch = on ? a.chan[tid] : 0;
+    s_b2[tid] = on ? a.fc2b[tid] : 0.f;
+    s_fa[tid] = (on && a.aff_a) ? a.aff_a[ch] : 1.f;
+    s_fb[tid] = (on && a.aff_b) ? a.aff_b[ch] : 0.f;
+    s_oo[tid] = on ? a.out_off[tid] : 0;
+    s_so[tid] = on ? a.st_off[tid] : 0;
+  }
+  if (warp == 0 && lane == 0) prefetch_tensormap(&tmX), prefetch_tensormap(&tmW1), prefetch_tensormap(&tmW2);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t T_X = tmem, T_ACC = tmem + 128, T_H = tmem + 256;
+
+  auto padded_row = [&](int row) {  // valid row (b, t, h) -> row of the padded activation grid
+    const int h = row % a.H, t = (row / a.H) % a.Tv, b = row / (a.H * a.Tv);
+    return (b * a.Tp + t) * a.Hp + h;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_full, (uint32_t)(TCP_W1 + 2 * 4 * N2 * 128));
+      for (int hl = 0; hl < 2; ++hl)
+        for (int s = 0; s < 2; ++s) tma_load_2d(sW1 + (hl * 2 + s) * 16384, &tmW1, &w_full, 32 * s, 128 * hl);
+      for (int hl = 0; hl < 2; ++hl)
+        for (int s = 0; s < 4; ++s) tma_load_2d(sW2 + (hl * 4 + s) * N2 * 128, &tmW2, &w_full, 32 * s, N2 * hl);
+      for (int it = 0; it < n_my; ++it) {
+        const int prow = padded_row(g + it * a.G);
+        const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
+        mbar_wait(&x_empty[sx], px ^ 1);
+        mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
+        tma_load_3d(sX + sx * TCP_XS, &tmX, &x_full[sx], 0, PT * j, prow);
+        tma_load_3d(sX + sx * TCP_XS + 16384, &tmX, &x_full[sx], 32, PT * j, prow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_tf32(128, 128, 0, 0), idesc2 = make_idesc_tf32(128, N2, 0, 0);
+      const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2);
+      mbar_wait(&w_full, 0);
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&xa_full, ph);
+        mbar_wait(&acc_free, ph ^ 1);
+        tc_fence_after();
+        auto d1 = [&](int hl, int ks) {
+          return make_smem_desc(w1 + (hl * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32, 0, 1024);
+        };
+        auto d2 = [&](int hl, int ks) {
+          return make_smem_desc(w2 + (hl * 4 + (ks >> 2)) * N2 * 128 + (ks & 3) * 32, 0, 1024);
+        };
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + 64 + ks * 8, d1(0, ks), idesc1, ks > 0);
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + ks * 8, d1(1, ks), idesc1, 1);
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + ks * 8, d1(0, ks), idesc1, 1);
+        umma_commit(&xa_empty);
+        umma_commit(&acc1_full);
+        mbar_wait(&h_full, ph);
+        tc_fence_after();
+        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2(0, ks), idesc2, ks > 0);
+        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + ks * 8, d2(1, ks), idesc2, 1);
+        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + ks * 8, d2(0, ks), idesc2, 1);
+        umma_commit(&acc2_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp - 4, p = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < n_my; ++it) {
+      const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
+      mbar_wait(&x_full[sx], px);
+      mbar_wait(&xa_empty, (it & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        const uint32_t base = smem_u32(sX) + sx * TCP_XS + half * 16384;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 u = lds128(base + sw128_off(p, c));
+          v[4 * c] = u.x, v[4 * c + 1] = u.y, v[4 * c + 2] = u.z, v[4 * c + 3] = u.w;
+        }
+        if (p >= PT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        tcp_st32(T_X + lane_addr + half * 32, v);
+        if (half == 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_empty[sx]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]);
+          v[i] = __float_as_uint(x - tf32_hi(x));
+        }
+        tcp_st32(T_X + 64 + lane_addr + half * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&xa_full);
+    }
+  } else if (warp >= 8) {
+    const int q = warp & 3, hh = (warp - 8) >> 2, p = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t ph = it & 1;
+      const int row = g + it * a.G;
+      const int h = row % a.H, t = (row / a.H) % a.Tv, b = row / (a.H * a.Tv);
+      const int w = PT * j + p;
+      // ---- epilogue 1: hidden = GELU(acc + b1) -> TMEM as the A operand of GEMM-2 (hi | lo)
+      mbar_wait(&acc1_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int col0 = hh * 64 + chunk * 32;
+        uint32_t v[32];
+        tmem_ld32(T_ACC + lane_addr + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(tcp_gelu(__uint_as_float(v[i]) + s_b1[col0 + i]));
+        tcp_st32(T_H + lane_addr + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]);
+          v[i] = __float_as_uint(x - tf32_hi(x));
+        }
+        tcp_st32(T_H + 128 + lane_addr + col0, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&h_full);
+      // ---- epilogue 2: + b2, rollout affine, scatter to the prediction slice and the next model input
+      mbar_wait(&acc2_full, ph);
+      tc_fence_after();
+      uint32_t v[32];
+      const bool have = hh * 32 < N2;
+      if (have) {
+        tmem_ld32(T_ACC + lane_addr + hh * 32, v);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free);
+      if (have && p < PT && w < a.W) {
+        const size_t po = (size_t)b * a.out_sB + (size_t)t * a.out_sT + ((size_t)h * a.W + w) * a.c_out;
+        const size_t ps = (size_t)b * a.st_sB + (size_t)t * a.st_sT + ((size_t)h * a.W + w) * a.c_in;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int f = hh * 32 + i;
+          if (f < a.Fout) {
+            const float y = fmaf(__uint_as_float(v[i]) + s_b2[f], s_fa[f], s_fb[f]);
+            a.out[po + s_oo[f]] = y;
+            if (a.state) a.state[ps + s_so[f]] = y;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+bool tc_proj_supported(const Geom& g, int Fout) { return g.Cp == 64 && Fout <= 64; }
+int tc_proj_n2(int Fout) { return round_up(Fout, 16); }
+void tc_proj_tile(int W, int* PT, int* NTW) {
+  *NTW = ceil_div(W, 128);
+  *PT = round_up(ceil_div(W, *NTW), 8);
+}
+int tc_make_proj_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g, int W) {
+  int PT, NTW;
+  tc_proj_tile(W, &PT, &NTW);
+  uint64_t dims[3] = {64, (uint64_t)g.Wp, (uint64_t)rows};
+  uint64_t strides[2] = {64 * 4, (uint64_t)g.Wp * 64 * 4};
+  uint32_t box[3] = {32, (uint32_t)PT, 1};
+  return encode_tensor_map(m, act, 3, dims, strides, box, 1);
+}
+int tc_make_fc1_map(CUtensorMap* m, const float* w) {  // [2*128 rows (hl, hid)][64]
+  uint64_t dims[2] = {64, 256};
+  uint64_t strides[1] = {64 * 4};
+  uint32_t box[2] = {32, 128};
+  return encode_tensor_map(m, w, 2, dims, strides, box, 1);
+}
+int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2) {  // [2*N2 rows (hl, f)][128]
+  uint64_t dims[2] = {128, (uint64_t)2 * N2};
+  uint64_t strides[1] = {128 * 4};
+  uint32_t box[2] = {32, (uint32_t)N2};
+  return encode_tensor_map(m, w, 2, dims, strides, box, 1);
+}
+
+int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+                   cudaStream_t st) {
+  TcProjArgs a{};
+  a.fc1b = pa.fc1b, a.fc2b = pa.fc2b, a.aff_a = pa.aff_a, a.aff_b = pa.aff_b;
+  a.chan = pa.chan, a.out_off = pa.out_off, a.st_off = pa.st_off, a.out = pa.out, a.state = pa.state;
+  a.rows = pa.B * pa.T * pa.H, a.Tv = pa.T, a.H = pa.H, a.W = pa.W, a.Tp = pa.Tp, a.Hp = pa.Hp;
+  tc_proj_tile(pa.W, &a.PT, &a.NTW);
+  a.G = std::max(1, std::min(148 / a.NTW, a.rows));
+  a.Fout = pa.Fout, a.N2 = tc_proj_n2(pa.Fout), a.c_out = pa.c_out, a.c_in = pa.c_in;
+  a.out_sB = pa.out_sB, a.out_sT = pa.out_sT, a.st_sB = pa.st_sB, a.st_sT = pa.st_sT;
+  B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
+  tc_proj_kernel<<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2);
+  B2_LAUNCHED("tc_proj_kernel");
+  return 0;
+}
+
+}  // namespace b200fno
