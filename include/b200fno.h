@@ -171,6 +171,11 @@ int b200fno_timing_collect(b200fno_plan_t* plan, double* ms /*[9]*/, int64_t* co
  * N in {32,64,128}, K in {32,64,96,128}; all pointers device fp32. */
 int b200fno_selftest_umma(int32_t mode_a, int32_t mode_b, int32_t out_tma, int32_t N, int32_t K, const float* A,
                           const float* B, float* D, void* stream);
+/* MMA issue-rate probe: `iters` back-to-back tcgen05.mma (M=128, N, K=8, tf32) from one CTA, cycling over
+ * `nacc` accumulators; writes the elapsed SM cycles to out_cycles_dev[0] (device int64).
+ * a_in_tmem: 1 = .ts form, 0 = .ss form; accumulate: 0 overwrites D (no read-modify-write). */
+int b200fno_selftest_mma_rate(int32_t N, int32_t iters, int32_t a_in_tmem, int32_t nacc, int32_t accumulate,
+                              long long* out_cycles_dev, void* stream);
 /* Host copy of truncated-DFT table `which` (0 fwdW, 1 fwdH, 2 fwdT, 3 invT, 4 invH,
  * 5 invW) for a transformed grid (t,h,w) -- the values the kernels multiply by.
  * Needs no device.  Writes at most `cap` floats to `out`, the row pitch to *ld and

@@ -20,7 +20,7 @@ SYMBOLS = (
     "b200fno_plan_bind", "b200fno_pack_weights", "b200fno_forward", "b200fno_rollout",
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
     "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
-    "b200fno_timing_collect", "b200fno_selftest_umma",
+    "b200fno_timing_collect", "b200fno_selftest_umma", "b200fno_selftest_mma_rate",
 )
 
 
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.b200fno_timing_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.b200fno_selftest_umma.restype = C.c_int
     L.b200fno_selftest_umma.argtypes = [i32] * 5 + [vp, vp, vp, vp]
+    L.b200fno_selftest_mma_rate.restype = C.c_int
+    L.b200fno_selftest_mma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     L.b200fno_algorithmic_bytes.restype = C.c_double
     L.b200fno_algorithmic_bytes.argtypes = [vp, i32]
     if L.b200fno_abi_version() != ABI_VERSION:

@@ -120,69 +120,82 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(&w_full, W_BYTES);
       for (int hl = 0; hl < 2; ++hl)
         for (int s = 0; s < 2; ++s) tma_load_2d(sW + hl * 16384 + s * 8192, &tmW, &w_full, 32 * s, 64 * hl);
-      for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
-        const int row = g + it * a.G;
-        const int sx = it % NSX, px = (it / NSX) & 1;
-        mbar_wait(&x_empty[sx], px ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
+      const int row = g + it * a.G;
+      const int sx = it % NSX, px = (it / NSX) & 1;
+      const int sd = it & 1, pd = (it >> 1) & 1;
+      mbar_wait(&x_empty[sx], px ^ 1);
+      mbar_wait(&d_empty[sd], pd ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
         tma_load_3d(sX + sx * XS_BYTES, &tmX, &x_full[sx], 0, PT * j, row);
         tma_load_3d(sX + sx * XS_BYTES + 16384, &tmX, &x_full[sx], 32, PT * j, row);
-        const int sd = it & 1, pd = (it >> 1) & 1;
-        mbar_wait(&d_empty[sd], pd ^ 1);
         mbar_arrive_expect_tx(&d_full[sd], (uint32_t)(2 * 2 * K2p * 128));
         tma_load_2d(sD + sd * DS_BYTES, &tmD, &d_full[sd], 0, row * 2 * K2p);
         tma_load_2d(sD + sd * DS_BYTES + 2 * K2p * 128, &tmD, &d_full[sd], 32, row * 2 * K2p);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_w = make_idesc_tf32(128, 64, 0, 0), idesc_d = make_idesc_tf32(128, 64, 0, 1);
-      const uint32_t w_addr = smem_u32(sW), d_addr = smem_u32(sD);
-      const int nk2 = K2p / 8;
-      mbar_wait(&w_full, 0);
-      for (int it = 0; it < n_my; ++it) {
-        const int t = it & 1, pt = (it >> 1) & 1;
-        mbar_wait(&a_full[t], pt);
-        if (MODE == MODE_LAYER) mbar_wait(&d_full[t], pt);
-        mbar_wait(&acc_empty[t], pt ^ 1);
-        tc_fence_after();
-        const uint32_t acc = T_ACC + t * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
+    // The whole warp runs the loop (uniform control flow and descriptors); one elected lane issues.
+    const uint32_t idesc_w = make_idesc_tf32(128, 64, 0, 0), idesc_d = make_idesc_tf32(128, 64, 0, 1);
+    const uint64_t dW_hi = make_smem_desc(smem_u32(sW), 0, 1024), dW_lo = make_smem_desc(smem_u32(sW) + 16384, 0, 1024);
+    const int nk2 = K2p / 8, nkl = a.nkl;
+    mbar_wait(&w_full, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int t = it & 1, pt = (it >> 1) & 1;
+      mbar_wait(&a_full[t], pt);
+      if (MODE == MODE_LAYER) mbar_wait(&d_full[t], pt);
+      mbar_wait(&acc_empty[t], pt ^ 1);
+      tc_fence_after();
+      const uint32_t acc = T_ACC + t * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
+      // descriptor "lo word" offsets are in 16-byte units: k-step ks of a K-major operand sits at
+      // sub-tile (ks/4) * 8192 B + (ks%4) * 32 B; of the MN-major D operand at ks * 8 rows * 128 B
+      const uint64_t dD_hi = make_smem_desc(smem_u32(sD) + t * DS_BYTES, 2 * K2p * 128, 512, LAYOUT_SW128_BASE32B);
+      const uint64_t dD_lo = dD_hi + (uint64_t)(K2p * 128 >> 4);
+      if (elect_one_sync()) {
         if (MODE == MODE_LIFT) {
-          for (int ks = 0; ks < a.nkl; ++ks) {
-            const uint64_t whi = make_smem_desc(w_addr + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
-            const uint64_t wlo = make_smem_desc(w_addr + 16384 + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
-            umma_tf32_ts(acc, Alo + ks * 8, whi, idesc_w, ks > 0);
-            umma_tf32_ts(acc, Ahi + ks * 8, wlo, idesc_w, 1);
-            umma_tf32_ts(acc, Ahi + ks * 8, whi, idesc_w, 1);
-          }
-          umma_commit(&a_empty[t]);
-          umma_commit(&acc_full[t]);
-          continue;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            if (ks < nkl) {
+              const uint64_t o = (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2);
+              umma_tf32_ts(acc, Alo + ks * 8, dW_hi + o, idesc_w, ks > 0);
+              umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + o, idesc_w, 1);
+              umma_tf32_ts(acc, Ahi + ks * 8, dW_hi + o, idesc_w, 1);
+            }
+        } else {
+          // small (lo) terms first, then the hi*hi terms
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32_ts(acc, Alo + ks * 8, dW_hi + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < nk2) umma_tf32_ts(acc, T_GLO + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < nk2) umma_tf32_ts(acc, T_GHI + ks * 8, dD_lo + (uint64_t)(ks * 64), idesc_d, 1);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32_ts(acc, Ahi + ks * 8, dW_hi + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < nk2) umma_tf32_ts(acc, T_GHI + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, 1);
+          umma_commit(&d_empty[t]);
         }
-        const uint32_t dbase = d_addr + t * DS_BYTES;
-        auto descW = [&](int hl, int ks) {
-          return make_smem_desc(w_addr + hl * 16384 + (ks >> 2) * 8192 + (ks & 3) * 32, 0, 1024);
-        };
-        auto descD = [&](int hl, int ks) {
-          return make_smem_desc(dbase + (hl * K2p + ks * 8) * 128, 2 * K2p * 128, 512, LAYOUT_SW128_BASE32B);
-        };
-        uint32_t accum = 0;
-        // small (lo) terms first, then the hi*hi terms
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Alo + ks * 8, descW(0, ks), idesc_w, accum), accum = 1;
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Ahi + ks * 8, descW(1, ks), idesc_w, 1);
-        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GLO + ks * 8, descD(0, ks), idesc_d, 1);
-        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GHI + ks * 8, descD(1, ks), idesc_d, 1);
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(acc, Ahi + ks * 8, descW(0, ks), idesc_w, 1);
-        for (int ks = 0; ks < nk2; ++ks) umma_tf32_ts(acc, T_GHI + ks * 8, descD(0, ks), idesc_d, 1);
         umma_commit(&a_empty[t]);
-        umma_commit(&d_empty[t]);
         umma_commit(&acc_full[t]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ split warps (A operand producers)

@@ -112,49 +112,67 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(&w_full, (uint32_t)(TCP_W1 + 2 * 4 * N2 * 128));
       for (int hl = 0; hl < 2; ++hl)
         for (int s = 0; s < 2; ++s) tma_load_2d(sW1 + (hl * 2 + s) * 16384, &tmW1, &w_full, 32 * s, 128 * hl);
       for (int hl = 0; hl < 2; ++hl)
         for (int s = 0; s < 4; ++s) tma_load_2d(sW2 + (hl * 4 + s) * N2 * 128, &tmW2, &w_full, 32 * s, N2 * hl);
-      for (int it = 0; it < n_my; ++it) {
-        const int prow = padded_row(g + it * a.G);
-        const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
-        mbar_wait(&x_empty[sx], px ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_my; ++it) {
+      const int prow = padded_row(g + it * a.G);
+      const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
+      mbar_wait(&x_empty[sx], px ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
         tma_load_3d(sX + sx * TCP_XS, &tmX, &x_full[sx], 0, PT * j, prow);
         tma_load_3d(sX + sx * TCP_XS + 16384, &tmX, &x_full[sx], 32, PT * j, prow);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_tf32(128, 128, 0, 0), idesc2 = make_idesc_tf32(128, N2, 0, 0);
-      const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2);
-      mbar_wait(&w_full, 0);
-      for (int it = 0; it < n_my; ++it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(&xa_full, ph);
-        mbar_wait(&acc_free, ph ^ 1);
-        tc_fence_after();
-        auto d1 = [&](int hl, int ks) {
-          return make_smem_desc(w1 + (hl * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32, 0, 1024);
-        };
-        auto d2 = [&](int hl, int ks) {
-          return make_smem_desc(w2 + (hl * 4 + (ks >> 2)) * N2 * 128 + (ks & 3) * 32, 0, 1024);
-        };
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + 64 + ks * 8, d1(0, ks), idesc1, ks > 0);
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + ks * 8, d1(1, ks), idesc1, 1);
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(T_ACC, T_X + ks * 8, d1(0, ks), idesc1, 1);
+    // whole warp runs the loop; one elected lane issues (see tc_common.cuh: elect_one_sync)
+    const uint32_t idesc1 = make_idesc_tf32(128, 128, 0, 0), idesc2 = make_idesc_tf32(128, N2, 0, 0);
+    const uint64_t d1_hi = make_smem_desc(smem_u32(sW1), 0, 1024), d1_lo = make_smem_desc(smem_u32(sW1) + 32768, 0, 1024);
+    const uint64_t d2_hi = make_smem_desc(smem_u32(sW2), 0, 1024),
+                   d2_lo = make_smem_desc(smem_u32(sW2) + 4 * N2 * 128, 0, 1024);
+    const uint64_t sub2 = (uint64_t)(N2 * 128 >> 4);  // one k-subtile of fc2 in 16-byte units
+    mbar_wait(&w_full, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t ph = it & 1;
+      mbar_wait(&xa_full, ph);
+      mbar_wait(&acc_free, ph ^ 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_tf32_ts(T_ACC, T_X + 64 + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_tf32_ts(T_ACC, T_X + ks * 8, d1_lo + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_tf32_ts(T_ACC, T_X + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, 1);
         umma_commit(&xa_empty);
         umma_commit(&acc1_full);
-        mbar_wait(&h_full, ph);
-        tc_fence_after();
-        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2(0, ks), idesc2, ks > 0);
-        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + ks * 8, d2(1, ks), idesc2, 1);
-        for (int ks = 0; ks < 16; ++ks) umma_tf32_ts(T_ACC, T_H + ks * 8, d2(0, ks), idesc2, 1);
+      }
+      __syncwarp();
+      mbar_wait(&h_full, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2_hi + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_tf32_ts(T_ACC, T_H + ks * 8, d2_lo + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, 1);
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_tf32_ts(T_ACC, T_H + ks * 8, d2_hi + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, 1);
         umma_commit(&acc2_full);
       }
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4, p = q * 32 + lane;

@@ -172,9 +172,70 @@ __global__ void __launch_bounds__(128) selftest_kernel(SelfTestArgs a, const __g
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// MMA issue-rate probe: one CTA issues `iters` back-to-back tcgen05.mma (M=128, N, K=8, kind::tf32) into one
+// accumulator and reports the elapsed SM cycles.  a_in_tmem: .ts form (A from TMEM) vs .ss (A from smem).
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int iters, int a_in_tmem, int nacc, int accumulate,
+                                                       long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) mbar_init(&bar, 1), fence_barrier_init();
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(128, N, 0, 0);
+    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    const uint32_t tb = tmem_base_s;
+    const uint64_t bd0 = make_smem_desc(sb, 0, 1024), ad0 = make_smem_desc(sa, 0, 1024);
+    const long long t0 = clock64();
+    if (elect_one_sync()) {
+      if (nacc == 1) {
+#pragma unroll 8
+        for (int i = 0; i < iters; ++i) {
+          if (a_in_tmem) umma_tf32_ts(tb, tb + 448 + (i & 7) * 8, bd0 + 2 * (i & 3), idesc, accumulate);
+          else umma_tf32_ss(tb, ad0 + 2 * (i & 3), bd0 + 2 * (i & 3), idesc, accumulate);
+        }
+      } else {
+#pragma unroll 8
+        for (int i = 0; i < iters; ++i) {
+          const uint32_t d = tb + (uint32_t)((i & (nacc - 1)) * N);
+          if (a_in_tmem) umma_tf32_ts(d, tb + 448 + (i & 7) * 8, bd0 + 2 * (i & 3), idesc, accumulate);
+          else umma_tf32_ss(d, ad0 + 2 * (i & 3), bd0 + 2 * (i & 3), idesc, accumulate);
+        }
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (tid == 32) out_cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace b200fno
 
 using namespace b200fno;
+
+extern "C" int b200fno_selftest_mma_rate(int32_t N, int32_t iters, int32_t a_in_tmem, int32_t nacc, int32_t accumulate,
+                                         long long* out_cycles_dev, void* stream) {
+  if (N % 16 || N < 16 || N > 256 || iters < 1 || !out_cycles_dev || nacc < 1 || nacc * N > 448) {
+    set_error("mma_rate: bad argument");
+    return B200FNO_EINVAL;
+  }
+  const int smem = 16384 + 32768 + 1024;
+  B2_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, iters, a_in_tmem, nacc, accumulate, out_cycles_dev);
+  B2_LAUNCHED("mma_rate_kernel");
+  return 0;
+}
 
 extern "C" int b200fno_selftest_umma(int32_t mode_a, int32_t mode_b, int32_t out_tma, int32_t N, int32_t K,
                                      const float* A, const float* B, float* D, void* stream) {
