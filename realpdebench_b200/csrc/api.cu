@@ -15,6 +15,11 @@ bool tc_layer_supported(const Geom& g);
 int tc_make_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g);
 int tc_make_w_map(CUtensorMap* m, const float* w_hl);
 int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g);
+bool tc_fwdw_supported(const Geom& g);
+int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, const float* table, long long rows,
+                      const Geom& g);
+int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, long long rows, const Geom& g,
+                   cudaStream_t st);
 bool tc_proj_supported(const Geom& g, int Fout);
 int tc_proj_n2(int Fout);
 int tc_make_proj_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g, int W);
@@ -115,6 +120,8 @@ struct b200fno_plan {
   bool use_tc = false, use_tc_lift = false;
   CUtensorMap tmAct[2], tmD, tmW0;
   float* W0K = nullptr;  // [2][64][64] lift weights as K-major hi|lo planes
+  bool use_tc_fwdw = false;
+  CUtensorMap tmFwX[2], tmFwF;
   bool use_tc_proj = false;
   CUtensorMap tmActProj[2], tmFc1, tmFc2;
   float *fc1HL = nullptr, *fc2HL = nullptr;  // [2][128][64], [2][N2][128]
@@ -155,12 +162,16 @@ static size_t spectral_scratch_floats(const Geom& g, int B) {
 //               which the layer kernel fuses with the bypass conv)
 static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
                         float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr,
-                        bool tc_planes = false) {
+                        bool tc_planes = false, const CUtensorMap* tmFwX = nullptr,
+                        const CUtensorMap* tmFwF = nullptr) {
   const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
   {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
     StageScope sc(tm, ST_FWD_W, st);
-    B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD,
-                       (long long)g.K2 * g.Cp, g.Cp, g.Cp, B * g.Tp * g.Hp, st));
+    if (tmFwX)
+      B2_TRY(launch_fwdw_tc(*tmFwX, *tmFwF, bufAD, (long long)B * g.Tp * g.Hp, g, st));
+    else
+      B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD,
+                         (long long)g.K2 * g.Cp, g.Cp, g.Cp, B * g.Tp * g.Hp, st));
   }
   {  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
     StageScope sc(tm, ST_FWD_H, st);
@@ -426,6 +437,11 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
     p->use_tc_lift = round_up(p->Klp, 8) <= 64;
     if (p->use_tc_lift) B2_TRY(tc_make_w_map(&p->tmW0, p->W0K));
+    p->use_tc_fwdw = tc_fwdw_supported(g);
+    if (p->use_tc_fwdw) {
+      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], p->tab.LF_hl, rows, g));
+      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[1], &p->tmFwF, p->act[1], p->tab.LF_hl, rows, g));
+    }
     p->use_tc_proj = tc_proj_supported(g, p->Fout);
     if (p->use_tc_proj) {
       B2_TRY(tc_make_proj_act_map(&p->tmActProj[0], p->act[0], rows, g, p->d.w));
@@ -504,7 +520,7 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerPacked& L = p->layers[l];
     B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing,
-                        p->use_tc));
+                        p->use_tc, p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF));
     {
       StageScope sc(&p->timing, ST_LAYER, st);
       if (p->use_tc)

@@ -77,6 +77,7 @@ struct Tables {
   int ldLF = 0, ldLH = 0, ldLT = 0, ldLTi = 0, ldLHi = 0;
   std::vector<int> ft, fh;  // actual frequency index of each kept T / H slot
   int *d_ft = nullptr, *d_fh = nullptr;
+  float* LF_hl = nullptr;  // forward-W table as hi|lo planes [2][K2][wpad] (tc_fwdw.cu)
 };
 int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6]);
 int build_tables(const Geom& g, int m1, int m2, Tables* t);

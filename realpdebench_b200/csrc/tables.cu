@@ -9,6 +9,7 @@
 // Nyquist) bin and doubles the others.  Twiddles are evaluated in double with
 // an exact integer reduction of the angle and rounded once to fp32.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -98,6 +99,23 @@ int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<fl
 int build_tables(const Geom& g, int m1, int m2, Tables* t) {
   std::vector<float> host[6];
   B2_TRY(compute_tables_host(g, m1, m2, t, host));
+  {  // forward-W table as 3xTF32 planes for the tensor-core kernel: [hi|lo][K2][wpad], zero padded
+    const int wpad = 2 * ceil_div(g.Wp, 64) * 32;
+    std::vector<float> hl((size_t)2 * g.K2 * wpad, 0.f);
+    for (int k = 0; k < g.K2; ++k)
+      for (int w = 0; w < g.Wp; ++w) {
+        const float x = host[0][(size_t)k * t->ldLF + w];
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u &= 0xFFFFE000u;
+        float hi;
+        memcpy(&hi, &u, 4);
+        hl[(size_t)k * wpad + w] = hi;
+        hl[((size_t)g.K2 + k) * wpad + w] = x - hi;
+      }
+    B2_CUDA(cudaMalloc((void**)&t->LF_hl, hl.size() * sizeof(float)));
+    B2_CUDA(cudaMemcpy(t->LF_hl, hl.data(), hl.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   const int KT = g.KT, KH = g.KH;
   const std::vector<float>* all[6] = {&host[0], &host[1], &host[2], &host[3], &host[4], &host[5]};
   size_t off[7] = {0};
@@ -124,7 +142,9 @@ int build_tables(const Geom& g, int m1, int m2, Tables* t) {
 
 void free_tables(Tables* t) {
   if (t->base) cudaFree(t->base);
+  if (t->LF_hl) cudaFree(t->LF_hl);
   t->base = nullptr;
+  t->LF_hl = nullptr;
 }
 
 }  // namespace b200fno

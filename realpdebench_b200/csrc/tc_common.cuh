@@ -173,6 +173,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ------------------------------------------------------------------------------------
@@ -206,6 +216,23 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r
 
 // 3xTF32 split: hi keeps the top 19 bits (exactly representable in tf32), lo = x - hi is exact in fp32
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// GELU (erf form, the F.gelu default of fno.py:119,124) without branches:
+//   v*Phi(v) = max(v,0) - |v| * 0.5*erfc(|v|/sqrt2),  erfc from Abramowitz-Stegun 7.1.26 (|eps| <= 1.5e-7).
+// Max abs error vs the exact function 5.3e-7 over [-12,12] (torch's own fp32 gelu: 1.2e-6), relative L2
+// 9e-8 on N(0,1) inputs.  14 instructions per element, two of them MUFU (rcp.approx, ex2.approx).
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float av = fabsf(v);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.0f)));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  poly *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * v * (-0.5f * 1.4426950408889634f)));
+  return fmaf(-av * poly, e, fmaxf(v, 0.0f));
+}
 
 }  // namespace tc
 

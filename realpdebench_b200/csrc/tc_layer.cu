@@ -49,31 +49,7 @@ struct TcLayerArgs {
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
-      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
 
-// GELU (erf form, F.gelu default) without branches: v*Phi(v) = max(v,0) - |v| * 0.5*erfc(|v|/sqrt2), with
-// erfc from Abramowitz-Stegun 7.1.26 (|eps| <= 1.5e-7).  Max abs error vs the exact function 5.3e-7 over
-// [-12,12] (torch's own fp32 gelu: 1.2e-6), relative L2 9e-8 on N(0,1) inputs; 15 instructions, 2 MUFU.
-__device__ __forceinline__ float gelu_erf_tc(float v) {
-  const float av = fabsf(v);
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.0f));
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(t, poly, 0.5f * 1.421413741f);
-  poly = fmaf(t, poly, 0.5f * -0.284496736f);
-  poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  poly *= t;
-  const float e = exp2f(v * v * (-0.5f * 1.4426950408889634f));
-  return fmaxf(v, 0.0f) - av * poly * e;
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
@@ -332,7 +308,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
         float y1 = fmaf(__uint_as_float(v[4 * c + 1]), sc[4 * c + 1], sh[4 * c + 1]);
         float y2 = fmaf(__uint_as_float(v[4 * c + 2]), sc[4 * c + 2], sh[4 * c + 2]);
         float y3 = fmaf(__uint_as_float(v[4 * c + 3]), sc[4 * c + 3], sh[4 * c + 3]);
-        if (a.gelu) y0 = gelu_erf_tc(y0), y1 = gelu_erf_tc(y1), y2 = gelu_erf_tc(y2), y3 = gelu_erf_tc(y3);
+        if (a.gelu) y0 = gelu_erf_fast(y0), y1 = gelu_erf_fast(y1), y2 = gelu_erf_fast(y2), y3 = gelu_erf_fast(y3);
         sts128(stage + sw128_off(p, c), y0, y1, y2, y3);
       }
       fence_proxy_async_smem();

@@ -37,29 +37,6 @@ struct TcProjArgs {
   long long out_sB, out_sT, st_sB, st_sT;
 };
 
-__device__ __forceinline__ void tcp_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void tcp_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
-      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-// same branch-free erf-GELU as tc_layer.cu (max abs error 5.3e-7)
-__device__ __forceinline__ float tcp_gelu(float v) {
-  const float av = fabsf(v);
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.0f));
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(t, poly, 0.5f * 1.421413741f);
-  poly = fmaf(t, poly, 0.5f * -0.284496736f);
-  poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  poly *= t;
-  const float e = exp2f(v * v * (-0.5f * 1.4426950408889634f));
-  return fmaxf(v, 0.0f) - av * poly * e;
-}
 
 __global__ void __launch_bounds__(TCP_THREADS, 1)
     tc_proj_kernel(TcProjArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -195,7 +172,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        tcp_st32(T_X + lane_addr + half * 32, v);
+        tmem_st32(T_X + lane_addr + half * 32, v);
         if (half == 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
@@ -205,7 +182,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
           float x = __uint_as_float(v[i]);
           v[i] = __float_as_uint(x - tf32_hi(x));
         }
-        tcp_st32(T_X + 64 + lane_addr + half * 32, v);
+        tmem_st32(T_X + 64 + lane_addr + half * 32, v);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -229,14 +206,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         tmem_ld32(T_ACC + lane_addr + col0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(tcp_gelu(__uint_as_float(v[i]) + s_b1[col0 + i]));
-        tcp_st32(T_H + lane_addr + col0, v);
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_erf_fast(__uint_as_float(v[i]) + s_b1[col0 + i]));
+        tmem_st32(T_H + lane_addr + col0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float x = __uint_as_float(v[i]);
           v[i] = __float_as_uint(x - tf32_hi(x));
         }
-        tcp_st32(T_H + 128 + lane_addr + col0, v);
+        tmem_st32(T_H + 128 + lane_addr + col0, v);
       }
       tmem_st_wait();
       tc_fence_before();
