@@ -27,6 +27,7 @@ int tc_make_fc1_map(CUtensorMap* m, const float* w);
 int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2);
 int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                    cudaStream_t st);
+int tc_lift_nkl(int Fin);
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
                    cudaStream_t st);
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
@@ -435,7 +436,7 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     B2_TRY(tc_make_act_map(&p->tmAct[1], p->act[1], rows, g));
     B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
-    p->use_tc_lift = round_up(p->Klp, 8) <= 64;
+    p->use_tc_lift = tc_lift_nkl(p->Fin) > 0;
     if (p->use_tc_lift) B2_TRY(tc_make_w_map(&p->tmW0, p->W0K));
     p->use_tc_fwdw = tc_fwdw_supported(g);
     if (p->use_tc_fwdw) {
@@ -467,8 +468,8 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   const int C = p->d.width, nf = p->Fin + p->ng;
   B2_TRY(launch_transpose_pad(w->fc0_w, C, nf, p->W0T, p->Klp, g.Cp, st));
   B2_TRY(launch_pad_copy(w->fc0_b, C, p->W0T + (size_t)nf * g.Cp, g.Cp, st));
-  if (p->use_tc_lift) {  // W0K[c][k] = W0T[k][c] (bias row included), then split in place into hi | lo
-    B2_TRY(launch_transpose_pad(p->W0T, p->Klp, g.Cp, p->W0K, 64, 64, st));
+  if (p->use_tc_lift) {  // K-major lift weights, then split in place into hi | lo
+    B2_TRY(launch_pack_w0k(w->fc0_w, w->fc0_b, C, p->Fin, p->ng, tc_lift_nkl(p->Fin), p->W0K, st));
     B2_TRY(launch_split_hl(p->W0K, 4096, p->W0K, p->W0K + 4096, st));
   }
   for (int l = 0; l < p->d.n_layers; ++l) {
@@ -509,7 +510,6 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   {
     StageScope sc(&p->timing, ST_LIFT, st);
     if (p->use_tc_lift) {
-      la.Klp = round_up(p->Klp, 8);
       B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st));
     } else {
       B2_TRY(launch_lift(la, st));

@@ -131,6 +131,8 @@ int launch_transpose_pad(const float* src, int rows, int cols, float* dst, int d
 int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v,
                    float eps, int C, int Cp, float* scale, float* shift, cudaStream_t st);
 int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st);
+int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int ng, int nkl, float* out,
+                    cudaStream_t st);
 int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st);  // 3xTF32 planes
 
 }  // namespace b200fno

@@ -112,6 +112,30 @@ int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st
   return 0;
 }
 
+// Lift weights for the tensor-core kernel, K-major [64 ch][64 k]: k < Fin input features, the last four
+// columns of the last K step (k = nkl*8-4 ..) = grid t, grid h, grid w, bias (fc0 columns Fin.., fno.py:107-108)
+__global__ void pack_w0k_kernel(const float* __restrict__ fc0_w, const float* __restrict__ fc0_b, int C, int Fin,
+                                int ng, int nkl, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int c = idx >> 6, k = idx & 63, e0 = nkl * 8 - 4, ld = Fin + ng;
+  float v = 0.f;
+  if (c < C) {
+    if (k < Fin) v = fc0_w[(size_t)c * ld + k];
+    else if (k >= e0 && k < e0 + 3) {
+      const int gi = k - e0 - (3 - ng);  // ng == 2: (h, w) only, the t slot stays zero
+      if (gi >= 0) v = fc0_w[(size_t)c * ld + Fin + gi];
+    } else if (k == e0 + 3) v = fc0_b[c];
+  }
+  out[idx] = v;
+}
+int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int ng, int nkl, float* out,
+                    cudaStream_t st) {
+  pack_w0k_kernel<<<16, 256, 0, st>>>(fc0_w, fc0_b, C, Fin, ng, nkl, out);
+  B2_LAUNCHED("pack_w0k_kernel");
+  return 0;
+}
+
 __global__ void split_hl_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

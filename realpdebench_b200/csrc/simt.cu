@@ -57,6 +57,18 @@ __device__ __forceinline__ float gelu_erf(float v) {  // F.gelu default (fno.py:
 // lmul: Out[g][m][n] = sum_k L[m][k] R[g][k][n]
 // grid (G, n tiles, m tiles); block TM*4 threads = (TM/4 row groups) x 16 column quads
 // ---------------------------------------------------------------------------
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills (out-of-range rows / columns)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int LM_STAGES = 4;  // K chunks in flight: these GEMMs are skinny, the K loop is latency-bound
+
 template <int TM>
 __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ L, int ldl, int M, int K,
                                                       const float* __restrict__ R, long long strideRg,
@@ -66,47 +78,45 @@ __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ 
   constexpr int NT = TM * 4;
   constexpr int A4 = TM * KC / 4 / NT;  // float4 per thread for the A tile (= 2)
   constexpr int B4 = KC * TN / 4 / NT;  // for the B tile (2 or 4)
-  __shared__ __align__(16) float As[TM * LDA];
-  __shared__ __align__(16) float Bs[KC * TN];
+  constexpr int STAGE = TM * LDA + KC * TN;
+  extern __shared__ __align__(16) float lm_smem[];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long g = blockIdx.x;
   const int n0 = blockIdx.y * TN, m0 = blockIdx.z * TM;
   const float* Rg = R + g * strideRg;
   float acc[4][4] = {};
-  float4 ra[A4], rb[B4];
-  auto fetch = [&](int k0) {
+  auto issue = [&](int chunk) {
+    const int k0 = chunk * KC;
+    float* As = lm_smem + (chunk % LM_STAGES) * STAGE;
+    float* Bs = As + TM * LDA;
 #pragma unroll
     for (int i = 0; i < A4; ++i) {
       int idx = tid + i * NT, mm = idx / (KC / 4), kk = (idx % (KC / 4)) * 4;
       int m = m0 + mm, k = k0 + kk;
-      ra[i] = (m < M && k < ldl) ? ldg4(L + (size_t)m * ldl + k) : zero4();
+      const bool ok = m < M && k < ldl;
+      cp_async16(As + mm * LDA + kk, ok ? L + (size_t)m * ldl + k : L, ok ? 16 : 0);
     }
 #pragma unroll
     for (int i = 0; i < B4; ++i) {
       int idx = tid + i * NT, kk = idx / (TN / 4), nn = (idx % (TN / 4)) * 4;
       int k = k0 + kk, n = n0 + nn;
-      rb[i] = (k < K && n < N) ? ldg4(Rg + (long long)k * strideRk + n) : zero4();
+      const bool ok = k < K && n < N;
+      cp_async16(Bs + kk * TN + nn, ok ? Rg + (long long)k * strideRk + n : R, ok ? 16 : 0);
     }
   };
-  auto stash = [&]() {
+  const int nchunks = (K + KC - 1) / KC;
 #pragma unroll
-    for (int i = 0; i < A4; ++i) {
-      int idx = tid + i * NT, mm = idx / (KC / 4), kk = (idx % (KC / 4)) * 4;
-      *reinterpret_cast<float4*>(As + mm * LDA + kk) = ra[i];
-    }
-#pragma unroll
-    for (int i = 0; i < B4; ++i) {
-      int idx = tid + i * NT, kk = idx / (TN / 4), nn = (idx % (TN / 4)) * 4;
-      *reinterpret_cast<float4*>(Bs + kk * TN + nn) = rb[i];
-    }
-  };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    stash();
-    __syncthreads();
-    if (k0 + KC < K) fetch(k0 + KC);
-    mma_chunk(acc, As + (ty * 4) * LDA, LDA, Bs + tx * 4, TN);
-    __syncthreads();
+  for (int s = 0; s < LM_STAGES - 1; ++s) {
+    if (s < nchunks) issue(s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<LM_STAGES - 2>();  // chunk c has landed
+    __syncthreads();                 // ... for every thread, and chunk c-1's buffer is free
+    if (c + LM_STAGES - 1 < nchunks) issue(c + LM_STAGES - 1);
+    cp_async_commit();
+    const float* As = lm_smem + (c % LM_STAGES) * STAGE;
+    mma_chunk(acc, As + (ty * 4) * LDA, LDA, As + TM * LDA + tx * 4, TN);
   }
   const int n = n0 + tx * 4;
   if (n < N) {
@@ -137,13 +147,16 @@ int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long
                 float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st, int mdiv,
                 long long strideOmLo, long long split_off) {
   if (G <= 0 || M <= 0) return 0;
+  constexpr int SM32 = LM_STAGES * (32 * LDA + KC * TN) * 4, SM64 = LM_STAGES * (64 * LDA + KC * TN) * 4;
   if (M <= 32) {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 32));
-    lmul_kernel<32><<<grid, 128, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
+    B2_CUDA(cudaFuncSetAttribute(lmul_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM32));
+    lmul_kernel<32><<<grid, 128, SM32, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
                                           strideOmLo, split_off);
   } else {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 64));
-    lmul_kernel<64><<<grid, 256, 0, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
+    B2_CUDA(cudaFuncSetAttribute(lmul_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64));
+    lmul_kernel<64><<<grid, 256, SM64, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
                                           strideOmLo, split_off);
   }
   B2_LAUNCHED("lmul_kernel");
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(256) modes_kernel(const float* __restrict__ S,
         const float* s0 = Ss + (bb * 2) * Cp;
         const float* s1 = Ss + ((two ? bb + 1 : bb) * 2) * Cp;
         float4 r0 = zero4(), i0 = zero4(), r1 = zero4(), i1 = zero4();
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < Cp; ++i) {
           const float4 wr = ldg4(Wm + ((size_t)i * 2 + 0) * Cp + q * 4);
           const float4 wi = ldg4(Wm + ((size_t)i * 2 + 1) * Cp + q * 4);

@@ -45,13 +45,15 @@ struct TcLayerArgs {
   const float *gt, *gh, *gw;
   int Tv, H, W, Tp, Hp, c_in, Fin, ng, nkl;  // nkl = K steps (Klp / 8)
   long long x_sB, x_sT;
+  // input tile staged by TMA (tmX = map over x as [B][T][H][W*c_in]): nb boxes of IB floats x NF frames
+  int in_tma, in_nb, in_IB, in_NF, in_box_floats;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 
 
-template <int MODE>
+template <int MODE, int NKL>  // NKL: K steps of the lift GEMM (0 in layer mode)
 __global__ void __launch_bounds__(TCL_THREADS, 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
@@ -85,6 +87,20 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
   if (tid < 64) s_scale[tid] = a.scale ? a.scale[tid] : 1.f, s_shift[tid] = a.shift ? a.shift[tid] : 0.f;
   if (MODE == MODE_LIFT && tid < 64) s_inoff[tid] = tid < a.Fin ? a.in_off[tid] : 0;
+  int* s_fchan = reinterpret_cast<int*>(sD);  // [64] channel of feature f
+  int* s_ffoff = s_fchan + 64;                // [64] frame offset of feature f inside a staged box
+  int* s_pbase = s_ffoff + 64;                // [c_in <= 8][128] offset of element (point p, channel c)
+  if (MODE == MODE_LIFT && a.in_tma) {
+    if (tid < 64) {
+      const int fr = tid / a.c_in;
+      s_fchan[tid] = tid - fr * a.c_in;
+      s_ffoff[tid] = (a.x_sT ? 0 : fr) * a.in_IB;
+    }
+    for (int i = tid; i < a.c_in * 128; i += TCL_THREADS) {
+      const int c = i >> 7, pp = i & 127, e = min(pp, PT - 1) * a.c_in + c, bx = e / a.in_IB;
+      s_pbase[i] = bx * a.in_box_floats + (e - bx * a.in_IB);
+    }
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX), prefetch_tensormap(&tmOut), prefetch_tensormap(&tmW), prefetch_tensormap(&tmD);
   }
@@ -102,6 +118,19 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
         for (int s = 0; s < 2; ++s) tma_load_2d(sW + hl * 16384 + s * 8192, &tmW, &w_full, 32 * s, 64 * hl);
     }
     __syncwarp();
+    for (int it = 0; MODE == MODE_LIFT && a.in_tma && it < n_my; ++it) {
+      const int row = g + it * a.G;
+      const int h = row % a.Hp, tt = (row / a.Hp) % a.Tp, b = row / (a.Hp * a.Tp);
+      const int sx = it % NSX, px = (it / NSX) & 1;
+      mbar_wait(&x_empty[sx], px ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&x_full[sx], (uint32_t)(a.in_nb * a.in_NF * a.in_IB * 4));
+        for (int bx = 0; bx < a.in_nb; ++bx)  // OOB coordinates (w >= W, h >= H, t >= T) are zero-filled
+          tma_load_4d(sX + sx * XS_BYTES + bx * a.in_box_floats * 4, &tmX, &x_full[sx],
+                      PT * j * a.c_in + bx * a.in_IB, h, a.x_sT ? tt : 0, b);
+      }
+      __syncwarp();
+    }
     for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
       const int row = g + it * a.G;
       const int sx = it % NSX, px = (it / NSX) & 1;
@@ -123,7 +152,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     // The whole warp runs the loop (uniform control flow and descriptors); one elected lane issues.
     const uint32_t idesc_w = make_idesc_tf32(128, 64, 0, 0), idesc_d = make_idesc_tf32(128, 64, 0, 1);
     const uint64_t dW_hi = make_smem_desc(smem_u32(sW), 0, 1024), dW_lo = make_smem_desc(smem_u32(sW) + 16384, 0, 1024);
-    const int nk2 = K2p / 8, nkl = a.nkl;
+    const int nk2 = K2p / 8;
     mbar_wait(&w_full, 0);
     for (int it = 0; it < n_my; ++it) {
       const int t = it & 1, pt = (it >> 1) & 1;
@@ -139,8 +168,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       if (elect_one_sync()) {
         if (MODE == MODE_LIFT) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            if (ks < nkl) {
+          for (int ks = 0; ks < NKL; ++ks) {
               const uint64_t o = (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2);
               umma_tf32_ts(acc, Alo + ks * 8, dW_hi + o, idesc_w, ks > 0);
               umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + o, idesc_w, 1);
@@ -193,23 +221,40 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       }
     }
     if (MODE == MODE_LIFT && n_my > 0) {
-      // A row of point p = [input features gathered from x | grid coordinates | 1 (bias)].
-      // The gather for tile it+1 is issued before tile it is converted, so its latency overlaps the
-      // TMEM stores and the wait for the A buffer instead of being exposed once per tile.
-      uint32_t r[64];
-      bool valid = false;
-      int h = 0, tt = 0, w = 0;
+      // A row of point p: columns [0, Fin) = input features gathered from x, the last four columns of the
+      // last K step = (grid t, grid h, grid w, 1 for the bias); W0K is packed to match.  The features of
+      // tile it+1 are fetched before tile it is converted, so their latency is off the critical path.
+      constexpr int NIN = NKL * 8 - 4;  // columns available to input features
+      uint32_t r[NIN > 0 ? NIN : 1];
+      float ex[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int f = 0; f < NIN; ++f) r[f] = 0u;
       auto gather = [&](int it) {
         const int row = g + it * a.G;
-        h = row % a.Hp, tt = (row / a.Hp) % a.Tp;
-        const int b = row / (a.Hp * a.Tp);
-        w = PT * j + p;
-        valid = p < PT && w < a.W && h < a.H && tt < a.Tv;
+        const int h = row % a.Hp, tt = (row / a.Hp) % a.Tp, b = row / (a.Hp * a.Tp);
+        const int w = PT * j + p;
+        const bool valid = p < PT && w < a.W && h < a.H && tt < a.Tv;
+        const float vf = valid ? 1.f : 0.f;
+        ex[0] = a.gt ? vf * __ldg(a.gt + min(tt, a.Tv - 1)) : 0.f;
+        ex[1] = vf * __ldg(a.gh + min(h, a.H - 1));
+        ex[2] = vf * __ldg(a.gw + min(w, a.W - 1));
+        ex[3] = vf;
+        if (a.in_tma) {  // TMA-staged tile; out-of-range points / rows were zero-filled by the copy engine
+          const int sx = it % NSX, px = (it / NSX) & 1;
+          mbar_wait(&x_full[sx], px);
+          const float* tile = reinterpret_cast<const float*>(sX + sx * XS_BYTES);
+#pragma unroll
+          for (int f = 0; f < NIN; ++f)
+            if (f < a.Fin) r[f] = __float_as_uint(tile[s_pbase[s_fchan[f] * 128 + p] + s_ffoff[f]]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_empty[sx]);
+          return;
+        }
         const float* xp = a.x + (size_t)b * a.x_sB + (size_t)min(tt, a.Tv - 1) * a.x_sT +
                           ((size_t)min(h, a.H - 1) * a.W + min(w, a.W - 1)) * a.c_in;
 #pragma unroll
-        for (int f = 0; f < 64; ++f)
-          if (f < a.Fin) r[f] = __float_as_uint(__ldg(xp + s_inoff[f]));
+        for (int f = 0; f < NIN; ++f)
+          if (f < a.Fin) r[f] = valid ? __float_as_uint(__ldg(xp + s_inoff[f])) : 0u;
       };
       gather(0);
       for (int it = 0; it < n_my; ++it) {
@@ -217,30 +262,18 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
         const uint32_t Ahi = T_A + t * 128 + lane_addr, Alo = Ahi + 64;
-        const float gtv = a.gt ? __ldg(a.gt + min(tt, a.Tv - 1)) : 0.f, ghv = __ldg(a.gh + min(h, a.H - 1)),
-                    gwv = __ldg(a.gw + min(w, a.W - 1));
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half * 32 >= a.nkl * 8) break;
-          uint32_t v[32];
+        for (int k0 = 0; k0 < NKL * 8; k0 += 8) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int f = half * 32 + i;
-            float x = 0.f;
-            if (f < a.Fin) x = __uint_as_float(r[f]);
-            else if (f < a.Fin + a.ng) {
-              const int gi = f - a.Fin + (a.gt ? 0 : 1);  // 0: t, 1: h, 2: w
-              x = gi == 0 ? gtv : (gi == 1 ? ghv : gwv);
-            } else if (f == a.Fin + a.ng) x = 1.f;
-            v[i] = valid ? __float_as_uint(x) : 0u;
+          for (int i = 0; i < 8; ++i) {
+            const int f = k0 + i;
+            const float x = f < NIN ? __uint_as_float(r[f < NIN ? f : 0]) : ex[f >= NIN ? f - NIN : 0];
+            hi[i] = __float_as_uint(x);
+            lo[i] = __float_as_uint(x - tf32_hi(x));
           }
-          tmem_st32(Ahi + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]);
-            v[i] = __float_as_uint(x - tf32_hi(x));
-          }
-          tmem_st32(Alo + half * 32, v);
+          tmem_st8(Ahi + k0, hi);
+          tmem_st8(Alo + k0, lo);
         }
         if (it + 1 < n_my) gather(it + 1);
         tmem_st_wait();
@@ -370,11 +403,13 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.Gt = Gt, a.scale = scale, a.shift = shift;
   a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
-  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
-  tc_layer_kernel<MODE_LAYER><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
+  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
+  tc_layer_kernel<MODE_LAYER, 0><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
   B2_LAUNCHED("tc_layer_kernel");
   return 0;
 }
+
+int tc_lift_nkl(int Fin);
 
 // Lift on tensor cores: act0 = [x | grid | 1] * W0K^T, zero in the pad region.  W0K: [2 (hi|lo)][64 ch][64 k].
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
@@ -385,12 +420,55 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
   a.x = la.x, a.in_off = la.in_off, a.gt = la.gt, a.gh = la.gh, a.gw = la.gw;
   a.Tv = la.T, a.H = la.H, a.W = la.W, a.Tp = g.Tp, a.Hp = g.Hp, a.c_in = la.c_in, a.Fin = la.Fin, a.ng = la.ng;
-  a.nkl = la.Klp / 8;
+  a.nkl = tc_lift_nkl(la.Fin);
   a.x_sB = la.x_sB, a.x_sT = la.x_sT;
-  B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
-  tc_layer_kernel<MODE_LIFT><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmOut, tmOut, tmW0, tmW0);
+  // Stage the input tile with TMA when its geometry allows (x viewed as [B][T][H][W*c_in] fp32).
+  CUtensorMap tmIn = tmOut;
+  {
+    const int seg = a.PT * la.c_in;                      // floats of one frame of one tile
+    const int nb = ceil_div(seg, 256), IB = seg / nb;    // boxes of IB <= 256 floats
+    const int NF = la.x_sT ? 1 : la.Fin / la.c_in;       // frames per box (2-D: all of them)
+    const int box_floats = round_up(NF * IB, 32);        // 128-byte aligned box regions
+    const bool ok = IB * nb == seg && IB % 4 == 0 && (la.W * la.c_in) % 4 == 0 && la.c_in <= 8 && NF <= 256 &&
+                    nb * box_floats * 4 <= XS_BYTES && ((uintptr_t)la.x & 15) == 0 &&
+                    (la.c_in * 128 + 128) * 4 <= 2 * DS_BYTES;
+    if (ok) {
+      const int T_frames = la.x_sT ? la.T : NF;
+      uint64_t dims[4] = {(uint64_t)la.W * la.c_in, (uint64_t)la.H, (uint64_t)T_frames, (uint64_t)la.B};
+      uint64_t strides[3] = {(uint64_t)la.W * la.c_in * 4, (uint64_t)la.H * la.W * la.c_in * 4,
+                             (uint64_t)T_frames * la.H * la.W * la.c_in * 4};
+      uint32_t box[4] = {(uint32_t)IB, 1, (uint32_t)NF, 1};
+      B2_TRY(encode_tensor_map(&tmIn, la.x, 4, dims, strides, box, 0));
+      a.in_tma = 1, a.in_nb = nb, a.in_IB = IB, a.in_NF = NF, a.in_box_floats = box_floats;
+    }
+  }
+  const int grid = a.NTW * a.G;
+#define B2_LIFT_CASE(N)                                                                                          \
+  case N:                                                                                                        \
+    B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LIFT, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 TCL_SMEM));                                                                     \
+    tc_layer_kernel<MODE_LIFT, N><<<grid, TCL_THREADS, TCL_SMEM, st>>>(a, tmIn, tmOut, tmW0, tmW0);              \
+    break;
+  switch (a.nkl) {
+    B2_LIFT_CASE(1)
+    B2_LIFT_CASE(2)
+    B2_LIFT_CASE(3)
+    B2_LIFT_CASE(8)
+    default:
+      set_error("tensor-core lift: unsupported K steps %d", a.nkl);
+      return B200FNO_EINVAL;
+  }
+#undef B2_LIFT_CASE
   B2_LAUNCHED("tc_lift_kernel");
   return 0;
+}
+
+// K steps of the lift GEMM for Fin input features (+ 4 fixed columns: grid t, h, w and the bias), or 0 if the
+// tensor-core lift has no instantiation for it
+int tc_lift_nkl(int Fin) {
+  const int n = ceil_div(Fin + 4, 8);
+  if (n <= 3) return n;
+  return n <= 8 ? 8 : 0;
 }
 
 }  // namespace b200fno
