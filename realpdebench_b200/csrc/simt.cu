@@ -148,7 +148,9 @@ int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long
                 long long strideOmLo, long long split_off) {
   if (G <= 0 || M <= 0) return 0;
   constexpr int SM32 = LM_STAGES * (32 * LDA + KC * TN) * 4, SM64 = LM_STAGES * (64 * LDA + KC * TN) * 4;
-  if (M <= 32) {
+  // 32-row tiles when M is small or when 64-row tiles would leave most SMs without a CTA
+  const long long ctas64 = (long long)G * ceil_div(N, TN) * ceil_div(M, 64);
+  if (M <= 32 || ctas64 < 2 * 148) {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 32));
     B2_CUDA(cudaFuncSetAttribute(lmul_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM32));
     lmul_kernel<32><<<grid, 128, SM32, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
@@ -170,17 +172,26 @@ int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long
 // ---------------------------------------------------------------------------
 constexpr int MODES_BCH = 32;  // batch entries staged per pass
 
+// Thread layout: threadIdx.x % nq = output-channel quad, the remaining 256/nq thread groups are split
+// between batch PAIRS and slices of the input-channel (i) loop.  With a small batch (the rollout runs
+// at B = 8) most groups would otherwise idle while a few threads walk all Cp input channels with two
+// dependent-latency weight loads per step; slicing i keeps every thread busy and 4x more loads in
+// flight.  Partial sums of the slices are reduced through shared memory.
 __global__ void __launch_bounds__(256) modes_kernel(const float* __restrict__ S, const float* __restrict__ Wpk,
                                                     float* __restrict__ O, int B, int NM, int Cp) {
-  extern __shared__ __align__(16) float Ss[];  // [MODES_BCH][2][Cp]
+  extern __shared__ __align__(16) float Ss[];  // [MODES_BCH][2][Cp] inputs, then [nsl][nb][2][Cp] partials
   const int mode = blockIdx.x;
-  const int OQ = Cp >> 2;                 // column quads
-  const int nq = min(OQ, 32);             // quads handled per sweep by threadIdx.x % nq
+  const int OQ = Cp >> 2;      // column quads
+  const int nq = min(OQ, 32);  // quads handled per sweep by threadIdx.x % nq
   const int tid = threadIdx.x;
   const int tx = tid % nq, ty = tid / nq, nty = 256 / nq;
+  float* Ps = Ss + MODES_BCH * 2 * Cp;
   const float* Wm = Wpk + (size_t)mode * Cp * 2 * Cp;
   for (int b0 = 0; b0 < B; b0 += MODES_BCH) {
     const int nb = min(MODES_BCH, B - b0);
+    const int nbp = (nb + 1) >> 1;                 // batch pairs in this pass
+    const int nsl = max(1, min(nty / nbp, 8));     // i-slices
+    const int isl = (Cp + nsl - 1) / nsl;          // input channels per slice
     __syncthreads();
     for (int idx = tid; idx < nb * 2 * OQ; idx += 256) {
       int q = idx % OQ, ri = (idx / OQ) & 1, bb = idx / (2 * OQ);
@@ -188,45 +199,61 @@ __global__ void __launch_bounds__(256) modes_kernel(const float* __restrict__ S,
           ldg4(S + (((size_t)(b0 + bb) * 2 + ri) * NM + mode) * Cp + q * 4);
     }
     __syncthreads();
-    for (int q = tx; q < OQ; q += nq) {
-      for (int bb = ty * 2; bb < nb; bb += nty * 2) {
-        const bool two = bb + 1 < nb;
-        const float* s0 = Ss + (bb * 2) * Cp;
-        const float* s1 = Ss + ((two ? bb + 1 : bb) * 2) * Cp;
-        float4 r0 = zero4(), i0 = zero4(), r1 = zero4(), i1 = zero4();
+    const int pair = ty % nbp, sl = ty / nbp;
+    if (sl < nsl) {
+      const int bb = pair * 2;
+      const bool two = bb + 1 < nb;
+      const float* s0 = Ss + (bb * 2) * Cp;
+      const float* s1 = Ss + ((two ? bb + 1 : bb) * 2) * Cp;
+      const int i0 = sl * isl, i1 = min(Cp, i0 + isl);
+      for (int q = tx; q < OQ; q += nq) {
+        float4 r0 = zero4(), im0 = zero4(), r1 = zero4(), im1 = zero4();
 #pragma unroll 8
-        for (int i = 0; i < Cp; ++i) {
+        for (int i = i0; i < i1; ++i) {
           const float4 wr = ldg4(Wm + ((size_t)i * 2 + 0) * Cp + q * 4);
           const float4 wi = ldg4(Wm + ((size_t)i * 2 + 1) * Cp + q * 4);
           const float ar = s0[i], ai = s0[Cp + i], br = s1[i], bi = s1[Cp + i];
           r0.x = fmaf(ar, wr.x, r0.x); r0.y = fmaf(ar, wr.y, r0.y); r0.z = fmaf(ar, wr.z, r0.z); r0.w = fmaf(ar, wr.w, r0.w);
           r0.x = fmaf(-ai, wi.x, r0.x); r0.y = fmaf(-ai, wi.y, r0.y); r0.z = fmaf(-ai, wi.z, r0.z); r0.w = fmaf(-ai, wi.w, r0.w);
-          i0.x = fmaf(ar, wi.x, i0.x); i0.y = fmaf(ar, wi.y, i0.y); i0.z = fmaf(ar, wi.z, i0.z); i0.w = fmaf(ar, wi.w, i0.w);
-          i0.x = fmaf(ai, wr.x, i0.x); i0.y = fmaf(ai, wr.y, i0.y); i0.z = fmaf(ai, wr.z, i0.z); i0.w = fmaf(ai, wr.w, i0.w);
+          im0.x = fmaf(ar, wi.x, im0.x); im0.y = fmaf(ar, wi.y, im0.y); im0.z = fmaf(ar, wi.z, im0.z); im0.w = fmaf(ar, wi.w, im0.w);
+          im0.x = fmaf(ai, wr.x, im0.x); im0.y = fmaf(ai, wr.y, im0.y); im0.z = fmaf(ai, wr.z, im0.z); im0.w = fmaf(ai, wr.w, im0.w);
           r1.x = fmaf(br, wr.x, r1.x); r1.y = fmaf(br, wr.y, r1.y); r1.z = fmaf(br, wr.z, r1.z); r1.w = fmaf(br, wr.w, r1.w);
           r1.x = fmaf(-bi, wi.x, r1.x); r1.y = fmaf(-bi, wi.y, r1.y); r1.z = fmaf(-bi, wi.z, r1.z); r1.w = fmaf(-bi, wi.w, r1.w);
-          i1.x = fmaf(br, wi.x, i1.x); i1.y = fmaf(br, wi.y, i1.y); i1.z = fmaf(br, wi.z, i1.z); i1.w = fmaf(br, wi.w, i1.w);
-          i1.x = fmaf(bi, wr.x, i1.x); i1.y = fmaf(bi, wr.y, i1.y); i1.z = fmaf(bi, wr.z, i1.z); i1.w = fmaf(bi, wr.w, i1.w);
+          im1.x = fmaf(br, wi.x, im1.x); im1.y = fmaf(br, wi.y, im1.y); im1.z = fmaf(br, wi.z, im1.z); im1.w = fmaf(br, wi.w, im1.w);
+          im1.x = fmaf(bi, wr.x, im1.x); im1.y = fmaf(bi, wr.y, im1.y); im1.z = fmaf(bi, wr.z, im1.z); im1.w = fmaf(bi, wr.w, im1.w);
         }
-        float* o0 = O + (((size_t)(b0 + bb) * 2) * NM + mode) * Cp + q * 4;
-        *reinterpret_cast<float4*>(o0) = r0;
-        *reinterpret_cast<float4*>(o0 + (size_t)NM * Cp) = i0;
+        float* pp = Ps + ((size_t)(sl * nb + bb) * 2) * Cp + q * 4;
+        *reinterpret_cast<float4*>(pp) = r0;
+        *reinterpret_cast<float4*>(pp + Cp) = im0;
         if (two) {
-          float* o1 = O + (((size_t)(b0 + bb + 1) * 2) * NM + mode) * Cp + q * 4;
-          *reinterpret_cast<float4*>(o1) = r1;
-          *reinterpret_cast<float4*>(o1 + (size_t)NM * Cp) = i1;
+          *reinterpret_cast<float4*>(pp + 2 * Cp) = r1;
+          *reinterpret_cast<float4*>(pp + 3 * Cp) = im1;
         }
       }
+    }
+    __syncthreads();
+    // reduce the i-slices and write O[b][ri][mode][:]
+    for (int idx = tid; idx < nb * 2 * OQ; idx += 256) {
+      int q = idx % OQ, ri = (idx / OQ) & 1, bb = idx / (2 * OQ);
+      float4 acc = zero4();
+      for (int s2 = 0; s2 < nsl; ++s2) {
+        const float4 v = *reinterpret_cast<const float4*>(Ps + ((size_t)(s2 * nb + bb) * 2 + ri) * Cp + q * 4);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(O + (((size_t)(b0 + bb) * 2 + ri) * NM + mode) * Cp + q * 4) = acc;
     }
   }
 }
 
 int launch_modes(const float* S, const float* Wpk, float* O, int B, int NM, int Cp, cudaStream_t st) {
-  size_t smem = (size_t)MODES_BCH * 2 * Cp * sizeof(float);
-  if (smem > 48 * 1024) {
+  // inputs + partial sums: nsl * nb <= max(MODES_BCH, 2 * thread groups) entries of 2*Cp floats
+  const int nq = std::min(Cp / 4, 32), nty = 256 / nq;
+  size_t smem = (size_t)(MODES_BCH + std::max(MODES_BCH, 2 * nty)) * 2 * Cp * sizeof(float);
+  if (smem > 200 * 1024) {
     set_error("modes kernel: width %d too large", Cp);
     return B200FNO_EINVAL;
   }
+  B2_CUDA(cudaFuncSetAttribute(modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   modes_kernel<<<NM, 256, smem, st>>>(S, Wpk, O, B, NM, Cp);
   B2_LAUNCHED("modes_kernel");
   return 0;
