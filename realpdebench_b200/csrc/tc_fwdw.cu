@@ -7,9 +7,11 @@
 // A chunk of 64 points x 64 channels x 2 rows is TMA-loaded (no swizzle); thread (row r, channel c)
 // reads its column of the tile (conflict-free, one 128 B shared-memory row per warp access), and
 // writes it as TMEM lane r*64+c - the transpose costs no extra shared-memory pass.  hi = raw fp32
-// (the MMA truncates to tf32), lo = x - trunc(x); B = the DFT table hi|lo, K-major, resident in smem.
+// (the MMA truncates to tf32), lo = x - trunc(x); B = the DFT table hi|lo, K-major; its 64-point chunk
+// rides in the same stage as the x chunk (an L2 hit shared by every CTA), which leaves shared memory for
+// a 4-deep ring: 128 KB of activation reads in flight per SM.
 //
-//   warp 0     TMA: table once, x chunks into a 2-stage ring
+//   warp 0     TMA: x chunk + table chunk into a 4-stage ring
 //   warp 1     MMA issuer (.ts form), 24 MMAs (N = 2*m3) per chunk, accumulating over the row
 //   warp 2     TMEM allocation
 //   warps 4-7  transpose + split: smem -> TMEM (x_hi | x_lo)
@@ -21,9 +23,11 @@ namespace b200fno {
 using namespace tc;
 
 constexpr int FW_THREADS = 384;
-constexpr int FW_NS = 2;          // x ring stages
+constexpr int FW_NS = 4;          // ring stages
 constexpr int FW_CH = 64;         // points per chunk
-constexpr int FW_XS = 32768;      // stage bytes: 2 channel halves x 2 rows x 64 points x 128 B
+constexpr int FW_XS = 32768;      // x part of a stage: 2 channel halves x 2 rows x 64 points x 128 B
+constexpr int FW_FS = 16384;      // table part: [hi|lo][2 sub-tiles of 32 points][K2 <= 32 rows][128 B]
+constexpr int FW_STAGE = FW_XS + FW_FS;
 
 struct FwdWArgs {
   float* out;  // [rows][K2][64]
@@ -34,17 +38,16 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
     tc_fwdw_kernel(FwdWArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sX = smem;
-  uint8_t* sF = sX + FW_NS * FW_XS;  // [hl][nsub][K2 rows][128 B]
-  __shared__ uint64_t f_full, x_full[FW_NS], x_empty[FW_NS], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+  uint8_t* sX = smem;  // FW_NS stages of [x chunk | table chunk]
+  __shared__ uint64_t x_full[FW_NS], x_empty[FW_NS], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K2 = a.K2, nchunk = a.nchunk, nsub = a.nsub;
+  const int K2 = a.K2, nchunk = a.nchunk;
   const int n_my = (int)blockIdx.x < a.npairs ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    mbar_init(&f_full, 1);
-    for (int i = 0; i < FW_NS; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
+    // a stage is free once the 4 transpose warps have read x AND the MMAs that read its table chunk are done
+    for (int i = 0; i < FW_NS; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 5);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
@@ -60,12 +63,6 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   const uint32_t T_ACC = tmem, T_A = tmem + 64;  // acc: 2 x 32 cols; A: 2 x (64 hi | 64 lo)
 
   if (warp == 0) {
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(&f_full, (uint32_t)(2 * nsub * K2 * 128));
-      for (int hl = 0; hl < 2; ++hl)
-        for (int s = 0; s < nsub; ++s) tma_load_2d(sF + (hl * nsub + s) * K2 * 128, &tmF, &f_full, 32 * s, K2 * hl);
-    }
-    __syncwarp();
     int cc = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       const int pair = blockIdx.x + ip * gridDim.x;
@@ -73,29 +70,33 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
         const int sx = cc % FW_NS, px = (cc / FW_NS) & 1;
         mbar_wait(&x_empty[sx], px ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&x_full[sx], FW_XS);
-          tma_load_3d(sX + sx * FW_XS, &tmX, &x_full[sx], 0, ch * FW_CH, 2 * pair);
-          tma_load_3d(sX + sx * FW_XS + 16384, &tmX, &x_full[sx], 32, ch * FW_CH, 2 * pair);
+          uint8_t* st = sX + sx * FW_STAGE;
+          mbar_arrive_expect_tx(&x_full[sx], (uint32_t)(FW_XS + 4 * K2 * 128));
+          tma_load_3d(st, &tmX, &x_full[sx], 0, ch * FW_CH, 2 * pair);
+          tma_load_3d(st + 16384, &tmX, &x_full[sx], 32, ch * FW_CH, 2 * pair);
+          for (int hl = 0; hl < 2; ++hl)
+            for (int s = 0; s < 2; ++s)
+              tma_load_2d(st + FW_XS + (hl * 2 + s) * K2 * 128, &tmF, &x_full[sx], 32 * (2 * ch + s), K2 * hl);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, K2, 0, 0);
-    const uint64_t dF_hi = make_smem_desc(smem_u32(sF), 0, 1024);
-    const uint64_t dF_lo = make_smem_desc(smem_u32(sF) + nsub * K2 * 128, 0, 1024);
     const uint64_t sub = (uint64_t)(K2 * 128 >> 4);  // one 32-point sub-tile of the table, 16-byte units
-    mbar_wait(&f_full, 0);
     int cc = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       const int ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_empty[ab], pab ^ 1);
       for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int t = cc & 1, pt = (cc >> 1) & 1;
+        const int t = cc & 1, pt = (cc >> 1) & 1, sx = cc % FW_NS;
+        mbar_wait(&x_full[sx], (cc / FW_NS) & 1);  // table chunk of this stage has landed
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
         const uint32_t acc = T_ACC + ab * 32, Ahi = T_A + t * 128, Alo = Ahi + 64;
-        const uint64_t o0 = (uint64_t)(ch * 2) * sub;
+        const uint64_t dF_hi = make_smem_desc(smem_u32(sX) + sx * FW_STAGE + FW_XS, 0, 1024);
+        const uint64_t dF_lo = dF_hi + 2 * sub;
+        const uint64_t o0 = 0;
         if (elect_one_sync()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
           for (int ks = 0; ks < 8; ++ks)
             umma_tf32_ts(acc, Ahi + ks * 8, dF_hi + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
           umma_commit(&a_empty[t]);
+          umma_commit(&x_empty[sx]);
           if (ch == nchunk - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
         mbar_wait(&x_full[sx], px);
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
-        const uint32_t src = smem_u32(sX) + sx * FW_XS + col_base;
+        const uint32_t src = smem_u32(sX) + sx * FW_STAGE + col_base;
         const uint32_t Ahi = T_A + t * 128 + lane_addr, Alo = Ahi + 64;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -178,11 +180,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-bool tc_fwdw_supported(const Geom& g) {
-  if (g.Cp != 64 || g.K2 != g.K2p || (g.K2 != 16 && g.K2 != 32)) return false;
-  const int nsub = 2 * ceil_div(g.Wp, FW_CH);
-  return FW_NS * FW_XS + 2 * nsub * g.K2 * 128 + 1024 <= 227 * 1024;
-}
+bool tc_fwdw_supported(const Geom& g) { return g.Cp == 64 && g.K2 == g.K2p && (g.K2 == 16 || g.K2 == 32); }
 int tc_fwdw_nsub(const Geom& g) { return 2 * ceil_div(g.Wp, FW_CH); }
 // table planes [2 (hi|lo)][K2 rows][nsub*32 points], zero padded
 size_t tc_fwdw_table_floats(const Geom& g) { return (size_t)2 * g.K2 * tc_fwdw_nsub(g) * 32; }
@@ -207,7 +205,7 @@ int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, l
   FwdWArgs a{};
   a.out = out, a.rows = (int)rows, a.npairs = (int)((rows + 1) / 2);
   a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2;
-  const int smem = FW_NS * FW_XS + 2 * a.nsub * g.K2 * 128 + 1024;
+  const int smem = FW_NS * FW_STAGE + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_fwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tc_fwdw_kernel<<<std::min(148, a.npairs), FW_THREADS, smem, st>>>(a, tmX, tmF);
   B2_LAUNCHED("tc_fwdw_kernel");

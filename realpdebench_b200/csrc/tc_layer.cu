@@ -6,7 +6,8 @@
 // (fno.py:114-119: x1 + x2 -> BatchNorm (eval) -> GELU).  One CTA per SM, persistent over the tiles
 // (row, j) of its fixed W-tile index j; a tile is PT <= 128 consecutive points of one (b,t,h) row.
 //
-//   warp 0     TMA producer: x tile (2 boxes of 32 channels) into a 3-stage ring, D[row] (hi|lo planes)
+//   warp 0     TMA producer: x tile (2 boxes of 32 channels) into a 3-stage ring
+//   warp 3     TMA producer: D[row] (hi|lo planes) into a 2-stage ring
 //   warp 1     MMA issuer: tcgen05.mma kind::tf32, A from TMEM (.ts form), B from shared memory
 //   warp 2     TMEM allocation (512 columns)
 //   warps 4-7  split: x tile smem -> registers -> TMEM as the A operand, hi = raw fp32 (the MMA truncates
@@ -134,13 +135,22 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
       const int row = g + it * a.G;
       const int sx = it % NSX, px = (it / NSX) & 1;
-      const int sd = it & 1, pd = (it >> 1) & 1;
       mbar_wait(&x_empty[sx], px ^ 1);
-      mbar_wait(&d_empty[sd], pd ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
         tma_load_3d(sX + sx * XS_BYTES, &tmX, &x_full[sx], 0, PT * j, row);
         tma_load_3d(sX + sx * XS_BYTES + 16384, &tmX, &x_full[sx], 32, PT * j, row);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ D producer (own warp: the x ring
+    // must be able to run its full depth ahead, not be tied to the 2-deep D ring)
+    for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
+      const int row = g + it * a.G;
+      const int sd = it & 1, pd = (it >> 1) & 1;
+      mbar_wait(&d_empty[sd], pd ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&d_full[sd], (uint32_t)(2 * 2 * K2p * 128));
         tma_load_2d(sD + sd * DS_BYTES, &tmD, &d_full[sd], 0, row * 2 * K2p);
         tma_load_2d(sD + sd * DS_BYTES + 2 * K2p * 128, &tmD, &d_full[sd], 32, row * 2 * K2p);
