@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   if (warp == 0) {
     int cc = 0;
     for (int ip = 0; ip < n_my; ++ip) {
-      const int pair = blockIdx.x + ip * gridDim.x;
+      const int pair = a.npairs - 1 - (blockIdx.x + ip * gridDim.x);  // reverse order: see launch_fwdw_tc
       for (int ch = 0; ch < nchunk; ++ch, ++cc) {
         const int sx = cc % FW_NS, px = (cc / FW_NS) & 1;
         mbar_wait(&x_empty[sx], px ^ 1);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int r = q >> 1, c = (q & 1) * 32 + lane;
     for (int ip = 0; ip < n_my; ++ip) {
-      const int pair = blockIdx.x + ip * gridDim.x, ab = ip & 1, pab = (ip >> 1) & 1;
+      const int pair = a.npairs - 1 - (blockIdx.x + ip * gridDim.x), ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_full[ab], pab);
       tc_fence_after();
       uint32_t v[32];
@@ -200,6 +200,9 @@ int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, cons
   return encode_tensor_map(tmF, table, 2, dims, strides, box, 1);
 }
 
+// Rows are visited from the LAST pair to the first: the kernel that produced this activation (lift / layer)
+// wrote it front to back, so its tail is still in the 126 MB L2 when this kernel starts; and this kernel
+// leaves the head of the activation in L2 for the layer kernel that reads it next, front to back.
 int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, long long rows, const Geom& g,
                    cudaStream_t st) {
   FwdWArgs a{};

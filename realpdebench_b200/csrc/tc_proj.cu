@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     }
     __syncwarp();
     for (int it = 0; it < n_my; ++it) {
-      const int prow = padded_row(g + it * a.G);
+      const int prow = padded_row(a.rows - 1 - (g + it * a.G));  // back to front: the tail is still in L2
       const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
       mbar_wait(&x_empty[sx], px ^ 1);
       if (elect_one_sync()) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ph = it & 1;
-      const int row = g + it * a.G;
+      const int row = a.rows - 1 - (g + it * a.G);
       const int h = row % a.H, t = (row / a.H) % a.Tv, b = row / (a.H * a.Tv);
       const int w = PT * j + p;
       // ---- epilogue 1: hidden = GELU(acc + b1) -> TMEM as the A operand of GEMM-2 (hi | lo)
