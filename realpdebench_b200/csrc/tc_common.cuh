@@ -116,6 +116,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {  // smem sources of all but the N newest groups are reusable
@@ -240,6 +247,56 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
   poly *= t;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * v * (-0.5f * 1.4426950408889634f)));
   return fmaf(-av * poly, e, fmaxf(v, 0.0f));
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): two elements per instruction ----------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_splat(float c) { return f2_pack(c, c); }
+
+// gelu_erf_fast on two values at once (same formula and accuracy; 9 instead of 14 instructions per element)
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  const f32x2 v = f2_pack(x0, x1), av = f2_pack(fabsf(x0), fabsf(x1));
+  float u0, u1, t0, t1, s0, s1, e0, e1;
+  f2_unpack(f2_fma(av, f2_splat(0.3275911f * 0.70710678118654752440f), f2_splat(1.0f)), u0, u1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const f32x2 t = f2_pack(t0, t1);
+  // -(0.5 * A&S coefficients): h = |v| * poly(t) is then -|v| * 0.5 * erfc(|v|/sqrt2) * exp(+v^2/2)
+  f32x2 poly = f2_fma(t, f2_splat(-0.5f * 1.061405429f), f2_splat(0.5f * 1.453152027f));
+  poly = f2_fma(t, poly, f2_splat(-0.5f * 1.421413741f));
+  poly = f2_fma(t, poly, f2_splat(0.5f * 0.284496736f));
+  poly = f2_fma(t, poly, f2_splat(-0.5f * 0.254829592f));
+  poly = f2_mul(poly, t);
+  f2_unpack(f2_mul(f2_mul(v, v), f2_splat(-0.5f * 1.4426950408889634f)), s0, s1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+  f2_unpack(f2_fma(f2_mul(av, poly), f2_pack(e0, e1), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
+}
+// 3xTF32 low parts of two values: x - trunc_tf32(x)
+__device__ __forceinline__ void tf32_lo2(uint32_t& r0, uint32_t& r1) {
+  const f32x2 x = f2_pack(__uint_as_float(r0), __uint_as_float(r1));
+  const f32x2 hi = f2_pack(__uint_as_float(r0 & 0xFFFFE000u), __uint_as_float(r1 & 0xFFFFE000u));
+  float a, b;
+  f2_unpack(f2_fma(hi, f2_splat(-1.0f), x), a, b);
+  r0 = __float_as_uint(a), r1 = __float_as_uint(b);
 }
 
 }  // namespace tc

@@ -141,10 +141,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
             if (lane == 0) mbar_arrive(&x_empty[sx]);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]);
-            v[i] = __float_as_uint(x - tf32_hi(x));
-          }
+          for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
           tmem_st32(Alo + half * 32, v);
         }
         tmem_st_wait();

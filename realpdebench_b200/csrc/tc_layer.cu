@@ -316,10 +316,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
           if (lane == 0) mbar_arrive(&x_empty[sx]);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]);
-          v[i] = __float_as_uint(x - tf32_hi(x));
-        }
+        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
         tmem_st32(Alo + half * 32, v);
       }
       tmem_st_wait();
@@ -347,11 +344,12 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       const uint32_t stage = smem_u32(sOut) + buf * OS_BYTES + half * 16384;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float y0 = fmaf(__uint_as_float(v[4 * c]), sc[4 * c], sh[4 * c]);
-        float y1 = fmaf(__uint_as_float(v[4 * c + 1]), sc[4 * c + 1], sh[4 * c + 1]);
-        float y2 = fmaf(__uint_as_float(v[4 * c + 2]), sc[4 * c + 2], sh[4 * c + 2]);
-        float y3 = fmaf(__uint_as_float(v[4 * c + 3]), sc[4 * c + 3], sh[4 * c + 3]);
-        if (a.gelu) y0 = gelu_erf_fast(y0), y1 = gelu_erf_fast(y1), y2 = gelu_erf_fast(y2), y3 = gelu_erf_fast(y3);
+        float y0, y1, y2, y3;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])),
+                         f2_pack(sc[4 * c], sc[4 * c + 1]), f2_pack(sh[4 * c], sh[4 * c + 1])), y0, y1);
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
+                         f2_pack(sc[4 * c + 2], sc[4 * c + 3]), f2_pack(sh[4 * c + 2], sh[4 * c + 3])), y2, y3);
+        if (a.gelu) gelu_erf_fast2(y0, y1), gelu_erf_fast2(y2, y3);
         sts128(stage + sw128_off(p, c), y0, y1, y2, y3);
       }
       fence_proxy_async_smem();

@@ -22,11 +22,12 @@ using namespace tc;
 
 constexpr int TCP_THREADS = 512;
 constexpr int TCP_EPI = 256;
-constexpr int TCP_NSX = 3;
+constexpr int TCP_NSX = 2;
 constexpr int TCP_XS = 32768;
+constexpr int TCP_ST = 32768;  // output staging tile (+ its index tables) for the TMA-store epilogue
 constexpr int TCP_W1 = 65536;  // [hl][2 k-subtiles][128 rows][128 B]
 constexpr int TCP_W2 = 65536;  // [hl][4 k-subtiles][N2 <= 64 rows][128 B]
-constexpr int TCP_SMEM = TCP_NSX * TCP_XS + TCP_W1 + TCP_W2 + 1024;
+constexpr int TCP_SMEM = TCP_NSX * TCP_XS + TCP_ST + TCP_W1 + TCP_W2 + 1024;
 
 struct TcProjArgs {
   const float *fc1b, *fc2b;      // [128], [>= Fout]
@@ -35,16 +36,27 @@ struct TcProjArgs {
   float *out, *state;
   int rows, Tv, H, W, Tp, Hp, PT, NTW, G, Fout, N2, c_out, c_in;
   long long out_sB, out_sT, st_sB, st_sT;
+  // TMA-store epilogue: the output tile is staged as [box][frame][OB floats] and stored with 4-D boxes over
+  // out viewed as [B][frames][H][W*c_out] (and the next-input state when c_in == c_out)
+  int out_tma, o_nb, o_OB, o_NF, o_box_floats, o_r, ndim3, st_tma;
 };
 
 
+__device__ __forceinline__ void tcp_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool OUT_TMA>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
     tc_proj_kernel(TcProjArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                   const __grid_constant__ CUtensorMap tmW2) {
+                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
+                   const __grid_constant__ CUtensorMap tmState) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;
-  uint8_t* sW1 = sX + TCP_NSX * TCP_XS;
+  uint8_t* sSt = sX + TCP_NSX * TCP_XS;
+  uint8_t* sW1 = sSt + TCP_ST;
+  int* s_fchan = reinterpret_cast<int*>(sSt + TCP_ST - 2048);  // [64] channel of feature f
+  int* s_ffoff = s_fchan + 64;                                  // [64] frame offset of feature f in a box
+  int* s_pbase = s_ffoff + 64;                                  // [c_out <= 3][128] offset of (point, channel)
   uint8_t* sW2 = sW1 + TCP_W1;
   __shared__ uint64_t x_full[TCP_NSX], x_empty[TCP_NSX], w_full, xa_full, xa_empty, acc1_full, h_full, acc2_full,
       acc_free;
@@ -73,10 +85,24 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     s_b2[tid] = on ? a.fc2b[tid] : 0.f;
     s_fa[tid] = (on && a.aff_a) ? a.aff_a[ch] : 1.f;
     s_fb[tid] = (on && a.aff_b) ? a.aff_b[ch] : 0.f;
+    if (OUT_TMA) {  // fold the fc2 bias into the affine: (acc + b2)*a + b = acc*a + (b2*a + b)
+      s_fb[tid] = fmaf(s_b2[tid], s_fa[tid], s_fb[tid]);
+      const int fr = a.ndim3 ? tid % a.o_r : tid / a.c_out;
+      s_fchan[tid] = on ? ch : 0;
+      s_ffoff[tid] = on ? fr * a.o_OB : 0;
+    }
     s_oo[tid] = on ? a.out_off[tid] : 0;
     s_so[tid] = on ? a.st_off[tid] : 0;
   }
-  if (warp == 0 && lane == 0) prefetch_tensormap(&tmX), prefetch_tensormap(&tmW1), prefetch_tensormap(&tmW2);
+  if (OUT_TMA)
+    for (int i = tid; i < a.c_out * 128; i += TCP_THREADS) {
+      const int c = i >> 7, pp = i & 127, e = min(pp, a.PT - 1) * a.c_out + c, bx = e / a.o_OB;
+      s_pbase[i] = bx * a.o_box_floats + (e - bx * a.o_OB);
+    }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmX), prefetch_tensormap(&tmW1), prefetch_tensormap(&tmW2);
+    if (OUT_TMA) prefetch_tensormap(&tmOut), prefetch_tensormap(&tmState);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -178,10 +204,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
           if (lane == 0) mbar_arrive(&x_empty[sx]);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]);
-          v[i] = __float_as_uint(x - tf32_hi(x));
-        }
+        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
         tmem_st32(T_X + 64 + lane_addr + half * 32, v);
       }
       tmem_st_wait();
@@ -206,13 +229,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         tmem_ld32(T_ACC + lane_addr + col0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_erf_fast(__uint_as_float(v[i]) + s_b1[col0 + i]));
+        for (int i = 0; i < 32; i += 2) {
+          float y0 = __uint_as_float(v[i]) + s_b1[col0 + i], y1 = __uint_as_float(v[i + 1]) + s_b1[col0 + i + 1];
+          gelu_erf_fast2(y0, y1);
+          v[i] = __float_as_uint(y0), v[i + 1] = __float_as_uint(y1);
+        }
         tmem_st32(T_H + lane_addr + col0, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]);
-          v[i] = __float_as_uint(x - tf32_hi(x));
-        }
+        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
         tmem_st32(T_H + 128 + lane_addr + col0, v);
       }
       tmem_st_wait();
@@ -229,7 +253,31 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       }
       tc_fence_before();
       mbar_arrive(&acc_free);
-      if (have && p < PT && w < a.W) {
+      if (OUT_TMA) {
+        const int etid = tid - 256;
+        if (etid == 0) tma_store_wait_read<0>();  // the previous tile's stores have read the staging buffer
+        tcp_named_bar(1, TCP_EPI);
+        float* stage = reinterpret_cast<float*>(sSt);
+        if (have && p < PT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int f = hh * 32 + i;
+            if (f < a.Fout)
+              stage[s_pbase[s_fchan[f] * 128 + p] + s_ffoff[f]] = fmaf(__uint_as_float(v[i]), s_fa[f], s_fb[f]);
+          }
+        }
+        fence_proxy_async_smem();
+        tcp_named_bar(1, TCP_EPI);
+        if (etid == 0) {
+          const int frame0 = a.ndim3 ? t * a.o_r : 0;
+          for (int bx = 0; bx < a.o_nb; ++bx) {
+            tma_store_4d(&tmOut, sSt + bx * a.o_box_floats * 4, PT * j * a.c_out + bx * a.o_OB, h, frame0, b);
+            if (a.st_tma)
+              tma_store_4d(&tmState, sSt + bx * a.o_box_floats * 4, PT * j * a.c_out + bx * a.o_OB, h, frame0, b);
+          }
+          tma_store_commit();
+        }
+      } else if (have && p < PT && w < a.W) {
         const size_t po = (size_t)b * a.out_sB + (size_t)t * a.out_sT + ((size_t)h * a.W + w) * a.c_out;
         const size_t ps = (size_t)b * a.st_sB + (size_t)t * a.st_sT + ((size_t)h * a.W + w) * a.c_in;
 #pragma unroll
@@ -243,6 +291,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         }
       }
     }
+    if (OUT_TMA && tid == 256) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -287,8 +336,42 @@ int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
   a.Fout = pa.Fout, a.N2 = tc_proj_n2(pa.Fout), a.c_out = pa.c_out, a.c_in = pa.c_in;
   a.out_sB = pa.out_sB, a.out_sT = pa.out_sT, a.st_sB = pa.st_sB, a.st_sT = pa.st_sT;
-  B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
-  tc_proj_kernel<<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2);
+  // TMA-store epilogue when the output geometry allows: out viewed as [B][frames][H][W*c_out] fp32
+  CUtensorMap tmOut = tmX, tmState = tmX;
+  {
+    const bool ndim3 = pa.out_sT != 0;
+    const int r = ndim3 ? (int)(pa.out_sT / ((long long)pa.H * pa.W * pa.c_out)) : 1;
+    const int NF = ndim3 ? r : pa.Fout / pa.c_out;            // frames written per tile
+    const int seg = a.PT * pa.c_out;                          // floats of one frame of one tile
+    const int nb = ceil_div(seg, 256), OB = seg / nb;
+    const int box_floats = round_up(NF * OB, 32);
+    const long long frame_elems = (long long)pa.H * pa.W * pa.c_out;
+    const bool ok = OB * nb == seg && OB % 4 == 0 && (pa.W * pa.c_out) % 4 == 0 && pa.c_out <= 3 && NF <= 256 &&
+                    NF * pa.c_out == (ndim3 ? pa.Fout : pa.Fout) && nb * box_floats * 4 <= TCP_ST - 2048 &&
+                    ((uintptr_t)pa.out & 15) == 0 && (pa.out_sB % 4) == 0 && pa.out_sB % frame_elems == 0;
+    if (ok) {
+      const long long frames_total = ndim3 ? (long long)pa.T * r : NF;  // frames this launch may touch per sample
+      uint64_t dims[4] = {(uint64_t)pa.W * pa.c_out, (uint64_t)pa.H, (uint64_t)frames_total, (uint64_t)pa.B};
+      uint64_t strides[3] = {(uint64_t)pa.W * pa.c_out * 4, (uint64_t)frame_elems * 4, (uint64_t)pa.out_sB * 4};
+      uint32_t box[4] = {(uint32_t)OB, 1, (uint32_t)NF, 1};
+      B2_TRY(encode_tensor_map(&tmOut, pa.out, 4, dims, strides, box, 0));
+      a.out_tma = 1, a.o_nb = nb, a.o_OB = OB, a.o_NF = NF, a.o_box_floats = box_floats, a.o_r = r, a.ndim3 = ndim3;
+      if (pa.state && pa.c_in == pa.c_out && ((uintptr_t)pa.state & 15) == 0 && pa.st_sB % 4 == 0) {
+        uint64_t sstr[3] = {(uint64_t)pa.W * pa.c_in * 4, (uint64_t)frame_elems * 4, (uint64_t)pa.st_sB * 4};
+        B2_TRY(encode_tensor_map(&tmState, pa.state, 4, dims, sstr, box, 0));
+        a.st_tma = 1;
+      } else if (pa.state) {
+        a.out_tma = 0;  // parameter channels interleave with the prediction: keep the scattered stores
+      }
+    }
+  }
+  if (a.out_tma) {
+    B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
+    tc_proj_kernel<true><<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2, tmOut, tmState);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
+    tc_proj_kernel<false><<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2, tmOut, tmState);
+  }
   B2_LAUNCHED("tc_proj_kernel");
   return 0;
 }
