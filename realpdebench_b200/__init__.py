@@ -6,6 +6,7 @@ Public surface (mirrors the reference names):
 * ``FNO2d`` / ``SpectralConv2d``  - the 2-D variant defined in SURVEY.md 8(c)
 * ``load_model``                  - realpdebench/model/load_model.py (+ ``fno2d``)
 * ``rollout``                     - realpdebench/eval.py:296-326 for one batch
+* ``rollout_stream``              - the same over a DataLoader, H2D of batch i+1 overlapped with batch i
 * ``install``                     - registers the above at ``realpdebench.model.fno``
                                     so the unmodified reference scripts use them
 
@@ -15,8 +16,8 @@ The arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of
 from .fno import FNO2d, FNO3d, SpectralConv2d, SpectralConv3d
 from .install import install, uninstall
 from .load_model import load_model
-from .rollout import rollout, rollout_affine
+from .rollout import rollout, rollout_affine, rollout_stream
 
-__all__ = ["FNO3d", "FNO2d", "SpectralConv3d", "SpectralConv2d", "load_model", "rollout", "rollout_affine",
+__all__ = ["FNO3d", "FNO2d", "SpectralConv3d", "SpectralConv2d", "load_model", "rollout", "rollout_affine", "rollout_stream",
            "install", "uninstall"]
 __version__ = "0.1.0"

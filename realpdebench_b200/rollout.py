@@ -49,3 +49,39 @@ def rollout(model, data_normalizer, input, target, N_autoregressive: int, unmeas
         _, pred = data_normalizer.postprocess(input, pred)  # eval.py:325
         _, target = data_normalizer.postprocess(input, target)  # eval.py:326
     return pred, target, loss, unmeasured_c
+
+
+def rollout_stream(model, data_normalizer, batches, N_autoregressive: int, unmeasured_c=None):
+    """The evaluation loop eval.py:296-343 over an iterable of HOST ``(input, target)`` batches.
+
+    Yields ``(pred, target, normalized_loss)`` per batch like :func:`rollout`, but stages the host->device
+    copy of batch i+1 on a side stream while batch i is being rolled out, so PCIe time overlaps compute
+    (pinned host tensors make the copies truly asynchronous; pageable ones still work, synchronously).
+    """
+    it = iter(batches)
+    try:
+        first = next(it)
+    except StopIteration:
+        return
+    device = next(model.parameters()).device
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def stage(batch):
+        inp, tgt = batch
+        with torch.cuda.stream(copy_stream):
+            d_in = inp.to(device, non_blocking=True)
+            d_tg = tgt.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d_in, d_tg, ev
+
+    nxt = stage(first)
+    while nxt is not None:
+        d_in, d_tg, ev = nxt
+        batch = next(it, None)
+        nxt = stage(batch) if batch is not None else None  # copy of the next batch overlaps this rollout
+        cur = torch.cuda.current_stream(device)
+        cur.wait_event(ev)
+        d_in.record_stream(cur), d_tg.record_stream(cur)
+        pred, target, loss, unmeasured_c = rollout(model, data_normalizer, d_in, d_tg, N_autoregressive, unmeasured_c)
+        yield pred, target, loss

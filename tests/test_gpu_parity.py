@@ -213,6 +213,18 @@ def test_rollout_golden(R, golden, case):
         assert O.rel_l2(step, g["states"][i + 1][..., :c_out]) < TOL
 
 
+def test_rollout_stream_matches_per_batch_rollout(R, golden):
+    g = golden("rollout.pt")["plain"]
+    m = make3d(R, g["ctor"], g["sd"])
+    norm = O.Normalizer(g["kind"], device=dev(), **g["stats"])
+    batches = [(g["input"].pin_memory(), g["target"].pin_memory()), (g["input"].flip(0).contiguous(), g["target"].flip(0).contiguous())]
+    want = [R.rollout(m, norm, a.to(dev()), b.to(dev()), g["n_auto"])[:3] for a, b in batches]
+    got = list(R.rollout_stream(m, norm, batches, g["n_auto"]))
+    assert len(got) == 2
+    for (p1, t1, l1), (p2, t2, l2) in zip(want, got):
+        assert torch.equal(p1, p2) and torch.equal(t1, t2) and l1 == l2
+
+
 def test_rollout_is_graph_capturable(R, golden):
     g = golden("rollout.pt")["controlled"]
     m = make3d(R, g["ctor"], g["sd"])
