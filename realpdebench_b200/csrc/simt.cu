@@ -17,9 +17,23 @@ constexpr int TN = 64;       // tile columns (channels)
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// acc[r][c] += sum_k As[r][k] * Bs[k][c]   for one K chunk resident in shared memory
+// acc[r][c] += sum_k As[r][k] * Bs[k][c]   for one K chunk resident in shared memory.
+// The 4x4 register tile is held as 4x2 packed fp32 pairs and updated with FFMA2 (sm_100 packed fp32:
+// two FMAs per instruction, the A value broadcast to both halves), halving the FMA instruction count.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void ffma2(f32x2_t& acc, f32x2_t a, f32x2_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ void mma_chunk(float (&acc)[4][4], const float* __restrict__ As, int lda,
                                           const float* __restrict__ Bs, int ldb) {
+  f32x2_t c[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) c[r][0] = pk2(acc[r][0], acc[r][1]), c[r][1] = pk2(acc[r][2], acc[r][3]);
 #pragma unroll
   for (int k = 0; k < KC; k += 4) {
     float4 a[4], b[4];
@@ -27,25 +41,23 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[4][4], const float* __res
     for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(As + r * lda + k);
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (k + j) * ldb);
+    f32x2_t blo[4], bhi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) blo[j] = pk2(b[j].x, b[j].y), bhi[j] = pk2(b[j].z, b[j].w);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      acc[r][0] = fmaf(a[r].x, b[0].x, acc[r][0]);
-      acc[r][1] = fmaf(a[r].x, b[0].y, acc[r][1]);
-      acc[r][2] = fmaf(a[r].x, b[0].z, acc[r][2]);
-      acc[r][3] = fmaf(a[r].x, b[0].w, acc[r][3]);
-      acc[r][0] = fmaf(a[r].y, b[1].x, acc[r][0]);
-      acc[r][1] = fmaf(a[r].y, b[1].y, acc[r][1]);
-      acc[r][2] = fmaf(a[r].y, b[1].z, acc[r][2]);
-      acc[r][3] = fmaf(a[r].y, b[1].w, acc[r][3]);
-      acc[r][0] = fmaf(a[r].z, b[2].x, acc[r][0]);
-      acc[r][1] = fmaf(a[r].z, b[2].y, acc[r][1]);
-      acc[r][2] = fmaf(a[r].z, b[2].z, acc[r][2]);
-      acc[r][3] = fmaf(a[r].z, b[2].w, acc[r][3]);
-      acc[r][0] = fmaf(a[r].w, b[3].x, acc[r][0]);
-      acc[r][1] = fmaf(a[r].w, b[3].y, acc[r][1]);
-      acc[r][2] = fmaf(a[r].w, b[3].z, acc[r][2]);
-      acc[r][3] = fmaf(a[r].w, b[3].w, acc[r][3]);
+      const f32x2_t a0 = pk2(a[r].x, a[r].x), a1 = pk2(a[r].y, a[r].y), a2 = pk2(a[r].z, a[r].z),
+                    a3 = pk2(a[r].w, a[r].w);
+      ffma2(c[r][0], a0, blo[0]), ffma2(c[r][1], a0, bhi[0]);
+      ffma2(c[r][0], a1, blo[1]), ffma2(c[r][1], a1, bhi[1]);
+      ffma2(c[r][0], a2, blo[2]), ffma2(c[r][1], a2, bhi[2]);
+      ffma2(c[r][0], a3, blo[3]), ffma2(c[r][1], a3, bhi[3]);
     }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[r][0]), "=f"(acc[r][1]) : "l"(c[r][0]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[r][2]), "=f"(acc[r][3]) : "l"(c[r][1]));
   }
 }
 

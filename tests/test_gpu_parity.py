@@ -194,6 +194,51 @@ def test_tc_rejected_for_unsupported_width(R, golden):
         m(g["x"].to(dev()))
 
 
+# ---------------------------------------------------------------- the other BASELINE.json configs (parity cases)
+def test_c4_combustion_shape_3d(R):
+    """BASELINE config C4: FNO-3D combustion 128x128x64 frames x 4 ch, modes (4,16,16), width 64 (one sample)."""
+    torch.manual_seed(40)
+    s = (64, 128, 128, 4)
+    sd = O.init_state(3, (4, 16, 16), 4, 64, s, s)
+    O.randomize_bn(sd, 4)
+    m = make3d(R, (4, 16, 16, 4, 64, s, s), sd)
+    x = torch.randn(1, *s)
+    y = m(x.to(dev())).cpu()
+    assert m.engine.resolved_impl() == "tc"
+    assert O.rel_l2(y, O.fno3d_forward(sd, x, s)) < TOL
+
+
+@pytest.mark.parametrize("k", [12, 16, 24, 32, 48, 64])
+def test_c5_mode_sweep_2d(R, k):
+    """BASELINE config C5: FNO-2D mode-count sweep at a 256^2 grid, one frame x 3 ch, width 64.
+    k <= 16 runs on the tensor-core kernels, larger mode counts on the FFMA kernels."""
+    torch.manual_seed(50 + k)
+    s = (1, 256, 256, 3)
+    sd = O.init_state(2, (k, k), 4, 64, s, s)
+    O.randomize_bn(sd, 5)
+    m = R.FNO2d(k, k, 4, 64, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    x = torch.randn(2, *s)
+    y = m(x.to(dev())).cpu()
+    assert m.engine.resolved_impl() == ("tc" if k in (12, 16) else "simt")
+    assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
+
+
+def test_c3_fsi_width128_2d_forward(R):
+    """BASELINE config C3 model (FNO-2D from configs/fsi/fno.yaml: modes (16,16), width 128), eval forward."""
+    torch.manual_seed(30)
+    s = (20, 64, 64, 3)
+    sd = O.init_state(2, (16, 16), 4, 128, s, s)
+    O.randomize_bn(sd, 6)
+    m = R.FNO2d(16, 16, 4, 128, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    x = torch.randn(3, *s)
+    y = m(x.to(dev())).cpu()
+    assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
+
+
 # ---------------------------------------------------------------- rollout
 @pytest.mark.parametrize("case", ["plain", "controlled", "range"])
 def test_rollout_golden(R, golden, case):
