@@ -121,6 +121,8 @@ struct b200fno_plan {
   bool use_tc = false, use_tc_lift = false;
   CUtensorMap tmAct[2], tmD, tmW0;
   float* W0K = nullptr;  // [2][64][64] lift weights as K-major hi|lo planes
+  bool use_tc_tmul = false;
+  CUtensorMap tmR_fwdH, tmR_fwdT, tmR_invT, tmR_invH;
   bool use_tc_fwdw = false;
   CUtensorMap tmFwX[2], tmFwF;
   bool use_tc_proj = false;
@@ -164,7 +166,8 @@ static size_t spectral_scratch_floats(const Geom& g, int B) {
 static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
                         float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr,
                         bool tc_planes = false, const CUtensorMap* tmFwX = nullptr,
-                        const CUtensorMap* tmFwF = nullptr) {
+                        const CUtensorMap* tmFwF = nullptr, const CUtensorMap* tmR4 = nullptr) {
+  // tmR4: data maps {fwdH, fwdT, invT, invH} when the H/T axis transforms run on the tensor cores
   const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
   {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
     StageScope sc(tm, ST_FWD_W, st);
@@ -177,14 +180,20 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   {  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
     StageScope sc(tm, ST_FWD_H, st);
     float* fwdH_out = g.ndim == 3 ? bufBC : bufS;
-    B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
-                       2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+    if (tmR4 && tab.tm_fwdH.ok)
+      B2_TRY(launch_tmul_tc(tab.tm_fwdH, tmR4[0], fwdH_out, B * g.Tp, 2LL * g.KH * n_hw, n_hw, 1, 0, 0, st));
+    else
+      B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
+                         2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
   }
   if (g.ndim == 3) {
     StageScope sc(tm, ST_FWD_T, st);
     const long long n_t = (long long)g.KH * n_hw;
-    B2_TRY(launch_lmul(tab.LT, tab.ldLT, 2 * g.KT, 2 * g.Tp, bufBC, (long long)g.Tp * 2 * n_t, n_t, bufS,
-                       2LL * g.KT * n_t, n_t, (int)n_t, B, st));
+    if (tmR4 && tab.tm_fwdT.ok)
+      B2_TRY(launch_tmul_tc(tab.tm_fwdT, tmR4[1], bufS, B, 2LL * g.KT * n_t, n_t, 1, 0, 0, st));
+    else
+      B2_TRY(launch_lmul(tab.LT, tab.ldLT, 2 * g.KT, 2 * g.Tp, bufBC, (long long)g.Tp * 2 * n_t, n_t, bufS,
+                         2LL * g.KT * n_t, n_t, (int)n_t, B, st));
   }
   {
     StageScope sc(tm, ST_MODES, st);
@@ -194,8 +203,11 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   if (g.ndim == 3) {
     StageScope sc(tm, ST_INV_T, st);
     const long long n_t = (long long)g.KH * n_hw;
-    B2_TRY(launch_lmul(tab.LTi, tab.ldLTi, 2 * g.Tp, 2 * g.KT, bufO, 2LL * g.KT * n_t, n_t, bufBC,
-                       (long long)g.Tp * 2 * n_t, n_t, (int)n_t, B, st));
+    if (tmR4 && tab.tm_invT.ok)
+      B2_TRY(launch_tmul_tc(tab.tm_invT, tmR4[2], bufBC, B, (long long)g.Tp * 2 * n_t, n_t, 1, 0, 0, st));
+    else
+      B2_TRY(launch_lmul(tab.LTi, tab.ldLTi, 2 * g.Tp, 2 * g.KT, bufO, 2LL * g.KT * n_t, n_t, bufBC,
+                         (long long)g.Tp * 2 * n_t, n_t, (int)n_t, B, st));
     invH_in = bufBC;
   }
   {
@@ -203,8 +215,12 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
     if (tc_planes) {
       // D[row=(g,h)][hl][k=(ri,kw)][o]: m = h*2+ri -> h * (2*K2p*Cp) + ri * (m3*Cp); lo plane at +K2p*Cp
       const long long plane = (long long)g.K2p * g.Cp;
-      B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
-                         (long long)g.Hp * 2 * plane, 2 * plane, (int)n_hw, B * g.Tp, st, 2, n_hw, plane));
+      if (tmR4 && tab.tm_invH.ok)
+        B2_TRY(launch_tmul_tc(tab.tm_invH, tmR4[3], bufAD, B * g.Tp, (long long)g.Hp * 2 * plane, 2 * plane, 2, n_hw,
+                              plane, st));
+      else
+        B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
+                           (long long)g.Hp * 2 * plane, 2 * plane, (int)n_hw, B * g.Tp, st, 2, n_hw, plane));
     } else {
       B2_TRY(launch_lmul(tab.LHi, tab.ldLHi, 2 * g.Hp, 2 * g.KH, invH_in, 2LL * g.KH * n_hw, n_hw, bufAD,
                          (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
@@ -438,6 +454,20 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
     p->use_tc_lift = tc_lift_nkl(p->Fin) > 0;
     if (p->use_tc_lift) B2_TRY(tc_make_w_map(&p->tmW0, p->W0K));
+    {  // H / T axis transforms on the tensor cores
+      const Tables& tb = p->tab;
+      const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw, GT = B * g.Tp;
+      p->use_tc_tmul = tb.tm_fwdH.ok || tb.tm_invH.ok || tb.tm_fwdT.ok || tb.tm_invT.ok;
+      if (tb.tm_fwdH.ok)
+        B2_TRY(tmul_make_data_map(&p->tmR_fwdH, p->bufAD, GT, 2 * g.Hp, n_hw, (long long)g.Hp * 2 * n_hw));
+      if (tb.tm_invH.ok)
+        B2_TRY(tmul_make_data_map(&p->tmR_invH, g.ndim == 3 ? p->bufBC : p->bufO, GT, 2 * g.KH, n_hw,
+                                  2LL * g.KH * n_hw));
+      if (tb.tm_fwdT.ok)
+        B2_TRY(tmul_make_data_map(&p->tmR_fwdT, p->bufBC, B, 2 * g.Tp, n_t, (long long)g.Tp * 2 * n_t));
+      if (tb.tm_invT.ok)
+        B2_TRY(tmul_make_data_map(&p->tmR_invT, p->bufO, B, 2 * g.KT, n_t, 2LL * g.KT * n_t));
+    }
     p->use_tc_fwdw = tc_fwdw_supported(g);
     if (p->use_tc_fwdw) {
       B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], p->tab.LF_hl, rows, g));
@@ -517,10 +547,12 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
   }
   int cur = 0;
   const long long rows = (long long)B * g.Tp * g.Hp;
+  const CUtensorMap tmR4[4] = {p->tmR_fwdH, p->tmR_fwdT, p->tmR_invT, p->tmR_invH};
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerPacked& L = p->layers[l];
     B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing,
-                        p->use_tc, p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF));
+                        p->use_tc, p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF,
+                        p->use_tc && p->use_tc_tmul ? tmR4 : nullptr));
     {
       StageScope sc(&p->timing, ST_LAYER, st);
       if (p->use_tc)

@@ -1,5 +1,6 @@
 // Shared declarations for the b200fno engine (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,6 +70,19 @@ struct Geom {
   size_t s_elems(int B) const { return (size_t)B * 2 * NM * Cp; }
 };
 
+// One small axis transform on the tensor cores (tc_tmul.cu): Out[g][m][n] = sum_k L[m][k] R[g][k][n]
+struct TmulPlan {
+  bool ok = false;
+  int M = 0, K = 0, N = 0, MT = 0, n_mt = 0, Mpad = 0, Kpad = 0, nchunk = 0, NS = 0, stage_bytes = 0;
+  float* table = nullptr;  // device, owned: hi|lo planes [2][Mpad][Kpad]
+  CUtensorMap tmL;
+};
+int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, int K, int N);
+void tmul_plan_free(TmulPlan* tp);
+int tmul_make_data_map(CUtensorMap* m, const float* R, int G, int K, int N, long long strideRg);
+int launch_tmul_tc(const TmulPlan& tp, const CUtensorMap& tmR, float* out, int G, long long sOg, long long sOm,
+                   int mdiv, long long sOmLo, long long split_off, cudaStream_t st);
+
 // Constant tables (device, fp32) for one geometry; see tables.cu for the values.
 struct Tables {
   float* base = nullptr;  // one cudaMalloc
@@ -78,6 +92,7 @@ struct Tables {
   std::vector<int> ft, fh;  // actual frequency index of each kept T / H slot
   int *d_ft = nullptr, *d_fh = nullptr;
   float* LF_hl = nullptr;  // forward-W table as hi|lo planes [2][K2][wpad] (tc_fwdw.cu)
+  TmulPlan tm_fwdH, tm_fwdT, tm_invT, tm_invH;  // tensor-core versions of the small axis transforms
 };
 int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6]);
 int build_tables(const Geom& g, int m1, int m2, Tables* t);

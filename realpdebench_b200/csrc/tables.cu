@@ -116,6 +116,15 @@ int build_tables(const Geom& g, int m1, int m2, Tables* t) {
     B2_CUDA(cudaMalloc((void**)&t->LF_hl, hl.size() * sizeof(float)));
     B2_CUDA(cudaMemcpy(t->LF_hl, hl.data(), hl.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
+  if (g.Cp == 64) {  // tensor-core plans for the H / T axis transforms (column counts are multiples of 128)
+    const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw;
+    B2_TRY(tmul_plan_build(&t->tm_fwdH, host[1], t->ldLH, 2 * g.KH, 2 * g.Hp, n_hw));
+    B2_TRY(tmul_plan_build(&t->tm_invH, host[4], t->ldLHi, 2 * g.Hp, 2 * g.KH, n_hw));
+    if (g.ndim == 3) {
+      B2_TRY(tmul_plan_build(&t->tm_fwdT, host[2], t->ldLT, 2 * g.KT, 2 * g.Tp, n_t));
+      B2_TRY(tmul_plan_build(&t->tm_invT, host[3], t->ldLTi, 2 * g.Tp, 2 * g.KT, n_t));
+    }
+  }
   const int KT = g.KT, KH = g.KH;
   const std::vector<float>* all[6] = {&host[0], &host[1], &host[2], &host[3], &host[4], &host[5]};
   size_t off[7] = {0};
@@ -143,6 +152,7 @@ int build_tables(const Geom& g, int m1, int m2, Tables* t) {
 void free_tables(Tables* t) {
   if (t->base) cudaFree(t->base);
   if (t->LF_hl) cudaFree(t->LF_hl);
+  tmul_plan_free(&t->tm_fwdH), tmul_plan_free(&t->tm_fwdT), tmul_plan_free(&t->tm_invT), tmul_plan_free(&t->tm_invH);
   t->base = nullptr;
   t->LF_hl = nullptr;
 }
