@@ -27,19 +27,19 @@ using namespace tc;
 
 constexpr int TCL_THREADS = 512;
 constexpr int EPI_THREADS = 256;
-constexpr int NSX = 3;
-constexpr int XS_BYTES = 32768;   // x stage: 2 sub-tiles (32 ch) x 128 rows x 128 B
-constexpr int OS_BYTES = 32768;   // output staging buffer
+constexpr int NSX_MAX = 4;
+constexpr int XS_MAX = 32768;     // x stage: 2 sub-tiles (32 ch) x PT <= 128 rows x 128 B = PT*256 bytes
+constexpr int TCL_BUDGET = 225 * 1024;  // dynamic shared memory the ring / staging layout may use
 constexpr int W_BYTES = 32768;    // conv weights hi | lo, each 2 sub-tiles x 64 rows x 128 B
 constexpr int DS_BYTES = 16384;   // D stage: 2 N-blocks x (2*K2p <= 64) k-rows x 128 B
-constexpr int TCL_SMEM = NSX * XS_BYTES + 2 * OS_BYTES + W_BYTES + 2 * DS_BYTES + 1024;
+constexpr int TCL_SMEM = TCL_BUDGET + 1024;
 
 enum { MODE_LAYER = 0, MODE_LIFT = 1 };
 
 struct TcLayerArgs {
   const float* Gt;  // [Wp][K2p] inverse-W table (scaled), fp32
   const float *scale, *shift;
-  int rows, Wp, PT, NTW, G, K2p, gelu;
+  int rows, Wp, PT, NTW, G, K2p, gelu, nsx;
   // MODE_LIFT only (fno.py:106-111): A tile = [input features | grid coordinates | 1] built from x
   const float* x;
   const int* in_off;
@@ -61,10 +61,12 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;
+  // stages are sized to the tile (PT points), so a 104-point tile gets a 4-deep x ring where a 128-point one gets 3
+  const int SUB = a.PT * 128, XS_BYTES = 2 * SUB, OS_BYTES = 2 * SUB, NSX = a.nsx;
   uint8_t* sOut = sX + NSX * XS_BYTES;
   uint8_t* sW = sOut + 2 * OS_BYTES;
   uint8_t* sD = sW + W_BYTES;
-  __shared__ uint64_t x_full[NSX], x_empty[NSX], d_full[2], d_empty[2], a_full[2], a_empty[2], acc_full[2],
+  __shared__ uint64_t x_full[NSX_MAX], x_empty[NSX_MAX], d_full[2], d_empty[2], a_full[2], a_empty[2], acc_full[2],
       acc_empty[2], w_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[64], s_shift[64];
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
   const int PT = a.PT, K2p = a.K2p;
 
   if (tid == 0) {
-    for (int i = 0; i < NSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
+    for (int i = 0; i < NSX_MAX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1), mbar_init(&d_empty[i], 1);
       mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&x_full[sx], (uint32_t)PT * 256u);
         tma_load_3d(sX + sx * XS_BYTES, &tmX, &x_full[sx], 0, PT * j, row);
-        tma_load_3d(sX + sx * XS_BYTES + 16384, &tmX, &x_full[sx], 32, PT * j, row);
+        tma_load_3d(sX + sx * XS_BYTES + SUB, &tmX, &x_full[sx], 32, PT * j, row);
       }
       __syncwarp();
     }
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        const uint32_t base = smem_u32(sX) + sx * XS_BYTES + half * 16384;
+        const uint32_t base = smem_u32(sX) + sx * XS_BYTES + half * SUB;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 u = lds128(base + sw128_off(p, c));
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       mbar_arrive(&acc_empty[t]);
       if (etid == 0) tma_store_wait_read<1>();  // the store that last used staging[buf] has read it
       named_bar_sync(1, EPI_THREADS);
-      const uint32_t stage = smem_u32(sOut) + buf * OS_BYTES + half * 16384;
+      const uint32_t stage = smem_u32(sOut) + buf * OS_BYTES + half * SUB;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float y0, y1, y2, y3;
@@ -350,14 +352,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
         f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
                          f2_pack(sc[4 * c + 2], sc[4 * c + 3]), f2_pack(sh[4 * c + 2], sh[4 * c + 3])), y2, y3);
         if (a.gelu) gelu_erf_fast2(y0, y1), gelu_erf_fast2(y2, y3);
-        sts128(stage + sw128_off(p, c), y0, y1, y2, y3);
+        if (p < PT) sts128(stage + sw128_off(p, c), y0, y1, y2, y3);  // rows >= PT lie outside the tile-sized buffer
       }
       fence_proxy_async_smem();
       named_bar_sync(1, EPI_THREADS);
       if (etid == 0) {
         const uint8_t* st = sOut + buf * OS_BYTES;
         tma_store_3d(&tmOut, st, 0, PT * j, row);
-        tma_store_3d(&tmOut, st + 16384, 32, PT * j, row);
+        tma_store_3d(&tmOut, st + SUB, 32, PT * j, row);
         tma_store_commit();
       }
     }
@@ -371,6 +373,12 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
 // ---------------------------------------------------------------------------------------------
 bool tc_layer_supported(const Geom& g) {
   return g.Cp == 64 && g.K2p % 8 == 0 && g.K2p <= 32 && ceil_div(g.Wp, 128) <= 148;
+}
+
+// x-ring depth that fits next to 2 staging buffers, the weights and the D ring
+int tc_layer_nsx(int PT) {
+  const int stage = PT * 256;
+  return std::max(2, std::min(NSX_MAX, (TCL_BUDGET - 2 * stage - W_BYTES - 2 * DS_BYTES) / stage));
 }
 
 int tc_layer_tile(const Geom& g, int* PT, int* NTW) {
@@ -411,6 +419,7 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.Gt = Gt, a.scale = scale, a.shift = shift;
   a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
+  a.nsx = tc_layer_nsx(a.PT);
   B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
   tc_layer_kernel<MODE_LAYER, 0><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
   B2_LAUNCHED("tc_layer_kernel");
@@ -426,6 +435,7 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
   tc_layer_tile(g, &a.PT, &a.NTW);
   a.rows = la.B * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
+  a.nsx = tc_layer_nsx(a.PT);
   a.x = la.x, a.in_off = la.in_off, a.gt = la.gt, a.gh = la.gh, a.gw = la.gw;
   a.Tv = la.T, a.H = la.H, a.W = la.W, a.Tp = g.Tp, a.Hp = g.Hp, a.c_in = la.c_in, a.Fin = la.Fin, a.ng = la.ng;
   a.nkl = tc_lift_nkl(la.Fin);
@@ -438,7 +448,7 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
     const int NF = la.x_sT ? 1 : la.Fin / la.c_in;       // frames per box (2-D: all of them)
     const int box_floats = round_up(NF * IB, 32);        // 128-byte aligned box regions
     const bool ok = IB * nb == seg && IB % 4 == 0 && (la.W * la.c_in) % 4 == 0 && la.c_in <= 8 && NF <= 256 &&
-                    nb * box_floats * 4 <= XS_BYTES && ((uintptr_t)la.x & 15) == 0 &&
+                    nb * box_floats * 4 <= 2 * a.PT * 128 && ((uintptr_t)la.x & 15) == 0 &&
                     (la.c_in * 128 + 128) * 4 <= 2 * DS_BYTES;
     if (ok) {
       const int T_frames = la.x_sT ? la.T : NF;
