@@ -10,8 +10,8 @@
 //   warp 0     TMA: fc1 / fc2 weights once (hi|lo, K-major), x tiles into a 3-stage ring
 //   warp 1     MMA issuer (A from TMEM, B from shared memory)
 //   warp 2     TMEM allocation
-//   warps 4-7  split: x tile -> TMEM (x_hi | x_lo)
-//   warps 8-15 epilogue 1 (bias, GELU, hi/lo -> TMEM) and epilogue 2 (bias, affine, scatter stores)
+//   warps 4-7  split: x tile -> TMEM (x_hi | x_lo), then 2 of the 8 sixteen-column chunks of epilogue 1
+//   warps 8-15 epilogue 1 (bias, GELU, hi/lo -> TMEM; 3 chunks each) and epilogue 2 (affine, staged TMA stores)
 //
 // TMEM columns: [0,128) x_hi|x_lo, [128,256) accumulator (GEMM-2 reuses it), [256,512) h_hi|h_lo.
 #include "common.cuh"
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     for (int i = 0; i < TCP_NSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
     mbar_init(&w_full, 1);
     mbar_init(&xa_full, 128), mbar_init(&xa_empty, 1);
-    mbar_init(&acc1_full, 1), mbar_init(&h_full, TCP_EPI);
+    mbar_init(&acc1_full, 1), mbar_init(&h_full, TCP_EPI + 128);
     mbar_init(&acc2_full, 1), mbar_init(&acc_free, TCP_EPI);
     fence_barrier_init();
   }
@@ -108,6 +108,23 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t T_X = tmem, T_ACC = tmem + 128, T_H = tmem + 256;
+
+  // epilogue 1 on 16 hidden columns of this thread's TMEM lane: GELU(acc + b1) -> (hi | lo) A operand of GEMM-2
+  auto epi1_chunk = [&](uint32_t lane_addr, int col0) {
+    uint32_t v[16];
+    tmem_ld16(T_ACC + lane_addr + col0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float y0 = __uint_as_float(v[i]) + s_b1[col0 + i], y1 = __uint_as_float(v[i + 1]) + s_b1[col0 + i + 1];
+      gelu_erf_fast2(y0, y1);
+      v[i] = __float_as_uint(y0), v[i + 1] = __float_as_uint(y1);
+    }
+    tmem_st16(T_H + lane_addr + col0, v);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) tf32_lo2(v[i], v[i + 1]);
+    tmem_st16(T_H + 128 + lane_addr + col0, v);
+  };
 
   auto padded_row = [&](int row) {  // valid row (b, t, h) -> row of the padded activation grid
     const int h = row % a.H, t = (row / a.H) % a.Tv, b = row / (a.H * a.Tv);
@@ -210,6 +227,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&xa_full);
+      // this warp's share of epilogue 1 for the same tile: hidden columns [96, 128)
+      mbar_wait(&acc1_full, it & 1);
+      tc_fence_after();
+      epi1_chunk(lane_addr, 96);
+      epi1_chunk(lane_addr, 112);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&h_full);
     }
   } else if (warp >= 8) {
     const int q = warp & 3, hh = (warp - 8) >> 2, p = q * 32 + lane;
@@ -223,22 +248,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       mbar_wait(&acc1_full, ph);
       tc_fence_after();
 #pragma unroll
-      for (int chunk = 0; chunk < 2; ++chunk) {
-        const int col0 = hh * 64 + chunk * 32;
-        uint32_t v[32];
-        tmem_ld32(T_ACC + lane_addr + col0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float y0 = __uint_as_float(v[i]) + s_b1[col0 + i], y1 = __uint_as_float(v[i + 1]) + s_b1[col0 + i + 1];
-          gelu_erf_fast2(y0, y1);
-          v[i] = __float_as_uint(y0), v[i + 1] = __float_as_uint(y1);
-        }
-        tmem_st32(T_H + lane_addr + col0, v);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
-        tmem_st32(T_H + 128 + lane_addr + col0, v);
-      }
+      for (int chunk = 0; chunk < 3; ++chunk) epi1_chunk(lane_addr, hh * 48 + chunk * 16);  // columns [0,48) / [48,96)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&h_full);
