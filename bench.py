@@ -107,6 +107,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic_bytes(kernel_substr="tc_layer_kernel<0"):
+    """dram read+write bytes per launch of the dominant kernel, from the committed ncu --set full summary
+    (profiles/r*_ncu_full.csv, newest round first); None if no capture is committed."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            h, units = rows[0], rows[1]
+            ik, ir, iw = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+                    for r in rows[2:] if kernel_substr in r[ik]]
+            if vals:
+                return sum(vals) / len(vals), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
 def build_state(ndim, modes, n_layers, width, s_in, s_out):
     """Reference-initialised weights (seed 0) + randomised BN statistics (SURVEY 8d synthetic inputs)."""
     from oracle import fno_oracle as O  # parameter initialisation recipe only (not on the timed path)
@@ -277,8 +297,11 @@ def run_engine(args):
         bytes_launch = 2.0 * B * tp * hp * wp * width * 4  # per layer, activation in + out
         dur = stages["layer"]["ms"] / stages["layer"]["launches"] * 1e-3
         ach = bytes_launch / dur / 1e9
+        traffic, traffic_src = (ncu_traffic_bytes() if wl == DEFAULT_WORKLOAD and not (args.batch or args.n_auto)
+                                else (None, None))
         roofline = {"bound": "hbm", "kernel": "fused Fourier-layer kernel (bypass conv + inverse-W DFT + BN + GELU)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
                     "avg_launch_ms": dur * 1e3}
     alg_bytes_step = n_auto * eng.algorithmic_bytes(B)
