@@ -151,6 +151,51 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
                           int32_t w, int32_t m1, int32_t m2, int32_t m3, const float* const* weights,
                           const float* x, float* y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training path ------------------------------------------------------- */
+/* Gradient outputs in the REFERENCE parameter layout (what torch's optimiser and
+ * DDP see): same fields as b200fno_weights_t without the BatchNorm buffers.
+ * Every non-NULL tensor is OVERWRITTEN with dL/dparam (not accumulated).
+ * spec_w gradients are complex64 [ci][co][m1][m2][m3] interleaved (d/dRe, d/dIm)
+ * = torch's .grad of a complex parameter viewed with view_as_real.  fc0_b is
+ * only written together with fc0_w. */
+typedef struct b200fno_grads {
+  float* fc0_w;
+  float* fc0_b;
+  float* const* spec_w;    /* n_layers * ncorner */
+  float* const* conv_w;    /* n_layers */
+  float* const* conv_b;
+  float* const* bn_weight;
+  float* const* bn_bias;
+  float* fc1_w;
+  float* fc1_b;
+  float* fc2_w;
+  float* fc2_b;
+} b200fno_grads_t;
+
+/* Device bytes the training path needs on top of the plan workspace: the saved
+ * layer inputs / pre-BatchNorm sums of one forward (2*n_layers+1 activations),
+ * two gradient activations and the projection / weight-gradient scratch. */
+size_t b200fno_train_workspace_bytes(const b200fno_plan_t* plan);
+int b200fno_train_bind(b200fno_plan_t* plan, void* workspace, size_t workspace_bytes);
+
+/* FNO3d.forward in .train() mode (fno.py:105-129 as called by train.py:328):
+ * BatchNorm uses the batch statistics of the PADDED tensor (fno.py:111,117).
+ * bn_running_mean / bn_running_var: n_layers device pointers updated in place
+ * like nn.BatchNorm3d (running = (1-momentum)*running + momentum*batch stat,
+ * unbiased variance); either array may be NULL (track_running_stats off).
+ * Keeps the activations needed by b200fno_train_backward in the training
+ * workspace (one forward outstanding per plan). */
+int b200fno_train_forward(b200fno_plan_t* plan, int32_t batch, const float* x, float* y,
+                          float* const* bn_running_mean, float* const* bn_running_var, float momentum,
+                          void* stream);
+
+/* Backward of the last b200fno_train_forward (autograd of fno.py:105-129 as
+ * driven by loss.backward(), train.py:329): dy = dL/dy [batch][t_out][h][w][c_out]
+ * -> parameter gradients.  The gradient w.r.t. the input x is not produced
+ * (train.py never needs it). */
+int b200fno_train_backward(b200fno_plan_t* plan, int32_t batch, const float* x, const float* dy,
+                           const b200fno_grads_t* grads, void* stream);
+
 /* ---- introspection used by bench.py / tests ------------------------------ */
 /* Kernels launched by this library on this thread since the last reset. */
 int64_t b200fno_launch_count(void);

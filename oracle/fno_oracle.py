@@ -7,6 +7,7 @@ tensors, the algorithm of
 * ``realpdebench/model/fno.py:66-143``  (FNO3d incl. ``get_grid``)
 * ``realpdebench/data/data_normalizer.py:6-62,98-130`` (the three normalisers)
 * ``realpdebench/eval.py:305-326``      (the autoregressive rollout loop)
+* ``realpdebench/train.py:321-334``     (one optimisation step; gradients by torch autograd of the restated forward)
 
 The arithmetic of that path lives in PyTorch/ATen (``torch.fft.rfftn/irfftn``,
 ``einsum``, ``conv3d``, ``batch_norm``, ``gelu``, ``linear``; torch is an
@@ -322,7 +323,66 @@ def rollout(model_fn: Callable[[Tensor], Tensor], norm: Normalizer, input: Tenso
     return pred, target, loss, preds
 
 
+# --------------------------------------------------------------------------
+# training step (train.py:321-334)
+# --------------------------------------------------------------------------
+PARAM_SUFFIXES = ("weight", "bias", "weights1", "weights2", "weights3", "weights4")
+
+
+def is_param(name: str) -> bool:
+    """state_dict entries that are nn.Parameters (everything but the BatchNorm buffers)."""
+    return name.rsplit(".", 1)[-1] in PARAM_SUFFIXES
+
+
+def train_loss_and_grads(ndim: int, sd: Dict[str, Tensor], x: Tensor, target: Tensor, shape_out: Sequence[int]):
+    """``loss = model.train_loss(input, target).mean(); loss.backward()`` (train.py:328-329, fno.py:131-133).
+
+    Returns ``(loss, grads, pred)``; ``sd``'s BatchNorm running buffers are updated in place like the
+    reference module in ``.train()`` mode (``num_batches_tracked`` included)."""
+    leaves = {k: (v.detach().clone().requires_grad_(True) if is_param(k) else v) for k, v in sd.items()}
+    fwd = fno3d_forward if ndim == 3 else fno2d_forward
+    pred = fwd(leaves, x, shape_out, training=True)
+    loss = F.mse_loss(pred, target, reduction="none").mean()  # utils/metrics.py:11-13 + train.py:328
+    loss.backward()
+    for k in sd:
+        if k.endswith("num_batches_tracked"):
+            sd[k] = sd[k] + 1
+    grads = {k: v.grad for k, v in leaves.items() if is_param(k)}
+    return float(loss.detach()), grads, pred.detach()
+
+
+def train_steps(ndim: int, sd: Dict[str, Tensor], batches, shape_out: Sequence[int], lr: float,
+                clip_grad_norm: float = 0.0, step_size: int = 100):
+    """train.py:321-334 for a list of normalised ``(input, target)`` batches: Adam + StepLR(gamma=0.5).
+    Updates ``sd`` in place; returns the list of losses."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if is_param(k)}
+    opt = torch.optim.Adam(list(params.values()), lr=lr)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=0.5)
+    fwd = fno3d_forward if ndim == 3 else fno2d_forward
+    losses = []
+    state = dict(sd)
+    for x, target in batches:
+        opt.zero_grad()
+        state.update(params)
+        loss = F.mse_loss(fwd(state, x, shape_out, training=True), target, reduction="none").mean()
+        loss.backward()
+        if clip_grad_norm > 0:
+            torch.nn.utils.clip_grad_norm_(list(params.values()), clip_grad_norm)
+        opt.step()
+        sched.step()
+        losses.append(float(loss.detach()))
+    for k, v in params.items():
+        sd[k] = v.detach()
+    for k in sd:
+        if not is_param(k) and not k.endswith("num_batches_tracked"):
+            sd[k] = state[k]
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = sd[k] + len(losses)
+    return losses
+
+
 def rel_l2(a: Tensor, b: Tensor) -> float:
     """||a-b||_2 / ||b||_2 over the whole tensor, in float64."""
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    a, b = (torch.view_as_real(t.detach()) if t.is_complex() else t.detach() for t in (a, b))
+    a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-300))

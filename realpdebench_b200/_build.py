@@ -36,22 +36,42 @@ def is_stale() -> bool:
     return any(os.path.getmtime(f) > t for f in deps)
 
 
+def _compile_one(nvcc, src, obj, verbose):
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-I", INCLUDE_DIR, "-c", src, "-o", obj]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {os.path.basename(src)} ({r.returncode}):\n{r.stdout}\n{r.stderr}")
+    return r.stderr
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu to an object (in parallel, only the stale ones) and link the shared library."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build realpdebench_b200/lib/libb200fno.so")
-    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE_DIR, "*.h"))
+    hdr_t = max(os.path.getmtime(f) for f in headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, obj))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        logs = list(ex.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+    if verbose:
+        print("\n".join(logs))
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE_DIR, "-o", tmp, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({r.returncode}):\n{r.stdout}\n{r.stderr}")
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError(f"link failed ({r.returncode}):\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
     return LIB_PATH

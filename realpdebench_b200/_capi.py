@@ -21,6 +21,7 @@ SYMBOLS = (
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
     "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
     "b200fno_timing_collect", "b200fno_selftest_umma", "b200fno_selftest_mma_rate",
+    "b200fno_train_workspace_bytes", "b200fno_train_bind", "b200fno_train_forward", "b200fno_train_backward",
 )
 
 
@@ -42,6 +43,11 @@ class Weights(C.Structure):
     _fields_ = [("fc0_w", _fp), ("fc0_b", _fp), ("spec_w", _fpp), ("conv_w", _fpp), ("conv_b", _fpp),
                 ("bn_weight", _fpp), ("bn_bias", _fpp), ("bn_mean", _fpp), ("bn_var", _fpp),
                 ("fc1_w", _fp), ("fc1_b", _fp), ("fc2_w", _fp), ("fc2_b", _fp)]
+
+
+class Grads(C.Structure):
+    _fields_ = [("fc0_w", _fp), ("fc0_b", _fp), ("spec_w", _fpp), ("conv_w", _fpp), ("conv_b", _fpp),
+                ("bn_weight", _fpp), ("bn_bias", _fpp), ("fc1_w", _fp), ("fc1_b", _fp), ("fc2_w", _fp), ("fc2_b", _fp)]
 
 
 _lib = None
@@ -99,6 +105,14 @@ def lib() -> C.CDLL:
     L.b200fno_selftest_umma.argtypes = [i32] * 5 + [vp, vp, vp, vp]
     L.b200fno_selftest_mma_rate.restype = C.c_int
     L.b200fno_selftest_mma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+    L.b200fno_train_workspace_bytes.restype = sz
+    L.b200fno_train_workspace_bytes.argtypes = [vp]
+    L.b200fno_train_bind.restype = C.c_int
+    L.b200fno_train_bind.argtypes = [vp, vp, sz]
+    L.b200fno_train_forward.restype = C.c_int
+    L.b200fno_train_forward.argtypes = [vp, i32, vp, vp, _fpp, _fpp, C.c_float, vp]
+    L.b200fno_train_backward.restype = C.c_int
+    L.b200fno_train_backward.argtypes = [vp, i32, vp, vp, C.POINTER(Grads), vp]
     L.b200fno_algorithmic_bytes.restype = C.c_double
     L.b200fno_algorithmic_bytes.argtypes = [vp, i32]
     if L.b200fno_abi_version() != ABI_VERSION:

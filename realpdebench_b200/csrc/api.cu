@@ -88,6 +88,7 @@ struct StageScope {
 
 struct LayerPacked {
   float *convT, *scale, *shift, *spec;
+  float *cbias, *gamma, *beta, *convW;  // training: conv bias, BN affine (unfolded), conv weight [o][i]
   float* convHL;  // [2][Cp][Cp]: conv weight [o][i] as 3xTF32 hi | lo planes (tensor-core path)
   CUtensorMap tmW;
 };
@@ -128,6 +129,21 @@ struct b200fno_plan {
   bool use_tc_proj = false;
   CUtensorMap tmActProj[2], tmFc1, tmFc2;
   float *fc1HL = nullptr, *fc2HL = nullptr;  // [2][128][64], [2][N2][128]
+  // training path (b200fno_train_*): untransposed projection weights + the caller-bound training workspace
+  float *fc1W = nullptr, *fc2W = nullptr;  // [128][Cp], [Fp][128]
+  struct Train {
+    bool bound = false, fwd_done = false;
+    int last_batch = 0;
+    std::vector<float*> xs, zs, Ssave, bnc;  // saved layer inputs x_0..x_L, pre-BN sums z_l, spectra S_l, BN coefficients
+    float *g0 = nullptr, *g1 = nullptr;      // gradient ping-pong [P][Cp]
+    float *Wadj = nullptr, *dWpk = nullptr;  // adjoint-packed spectral weights, packed spectral gradient
+    float *G = nullptr, *dH = nullptr, *dF = nullptr;  // projection scratch [P][128], [P][128], [P][Fp] (G also = lift features)
+    double* stats = nullptr;                 // [2][Cp]
+    // transposed tables (device, owned by the plan)
+    float* tbase = nullptr;
+    const float *GtT = nullptr, *LHiT = nullptr, *LTiT = nullptr, *LTT = nullptr, *LHT = nullptr, *LFT = nullptr;
+    int *slot_t = nullptr, *slot_h = nullptr;
+  } tr;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -356,6 +372,7 @@ int b200fno_plan_create(const b200fno_desc_t* d, b200fno_plan_t** out) {
 int b200fno_plan_destroy(b200fno_plan_t* p) {
   if (!p) return 0;
   free_tables(&p->tab);
+  if (p->tr.tbase) cudaFree(p->tr.tbase);
   if (p->d_grid) cudaFree(p->d_grid);
   if (p->d_int) cudaFree(p->d_int);
   delete p;
@@ -398,6 +415,9 @@ static size_t packed_floats(const b200fno_plan* p) {
   n += (size_t)p->d.n_layers *
        (3 * align_up((size_t)g.Cp * g.Cp, 64) + 2 * align_up(g.Cp, 64) + align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64));
   n += align_up((size_t)g.Cp * 128, 64) + 128 + align_up((size_t)128 * p->Fp, 64) + align_up(p->Fp, 64);
+  // training copies: per layer conv bias, BN weight, BN bias, conv weight [o][i]; fc1 [128][Cp], fc2 [Fp][128]
+  n += (size_t)p->d.n_layers * (3 * align_up(g.Cp, 64) + align_up((size_t)g.Cp * g.Cp, 64));
+  n += align_up((size_t)128 * g.Cp, 64) + align_up((size_t)p->Fp * 128, 64);
   return n;
 }
 size_t b200fno_plan_packed_bytes(const b200fno_plan_t* p) { return p ? packed_floats(p) * sizeof(float) : 0; }
@@ -443,7 +463,15 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   p->fc1T = q, q += align_up((size_t)g.Cp * 128, 64);
   p->fc1b = q, q += 128;
   p->fc2T = q, q += align_up((size_t)128 * p->Fp, 64);
-  p->fc2b = q;
+  p->fc2b = q, q += align_up(p->Fp, 64);
+  for (auto& L : p->layers) {
+    L.cbias = q, q += align_up(g.Cp, 64);
+    L.gamma = q, q += align_up(g.Cp, 64);
+    L.beta = q, q += align_up(g.Cp, 64);
+    L.convW = q, q += align_up((size_t)g.Cp * g.Cp, 64);
+  }
+  p->fc1W = q, q += align_up((size_t)128 * g.Cp, 64);
+  p->fc2W = q;
   p->weights_ready = false;
   p->use_tc = p->impl_request != B200FNO_IMPL_SIMT && tc_layer_supported(g) && g.K2 == g.K2p;
   if (p->use_tc) {
@@ -511,7 +539,13 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
                           g.Cp, L.scale, L.shift, st));
     B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, L.spec, g, C, C, p->d.modes1,
                                 p->d.modes2, p->tab.d_ft, p->tab.d_fh, st));
+    B2_TRY(launch_pad_copy(w->conv_b[l], C, L.cbias, g.Cp, st));
+    B2_TRY(launch_pad_copy(w->bn_weight[l], C, L.gamma, g.Cp, st));
+    B2_TRY(launch_pad_copy(w->bn_bias[l], C, L.beta, g.Cp, st));
+    B2_TRY(launch_pad2d(w->conv_w[l], C, C, L.convW, g.Cp, g.Cp, st));
   }
+  B2_TRY(launch_pad2d(w->fc1_w, 128, C, p->fc1W, 128, g.Cp, st));
+  B2_TRY(launch_pad2d(w->fc2_w, p->Fout, 128, p->fc2W, p->Fp, 128, st));
   B2_TRY(launch_transpose_pad(w->fc1_w, 128, C, p->fc1T, g.Cp, 128, st));
   B2_TRY(launch_pad_copy(w->fc1_b, 128, p->fc1b, 128, st));
   B2_TRY(launch_transpose_pad(w->fc2_w, p->Fout, 128, p->fc2T, 128, p->Fp, st));
@@ -526,17 +560,24 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   return 0;
 }
 
-// lift + L Fourier layers; leaves the last layer's output in *final_act
-static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final_act, cudaStream_t st) {
+static LiftArgs make_lift_args(const b200fno_plan* p, int B, const float* x, float* act) {
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
   LiftArgs la{};
-  la.x = x, la.act = p->act[0], la.W0T = p->W0T, la.in_off = p->in_off;
+  la.x = x, la.act = act, la.W0T = p->W0T, la.in_off = p->in_off;
   la.gt = p->gt, la.gh = p->gh, la.gw = p->gw;
   la.B = B, la.T = p->Tv, la.H = d.h, la.W = d.w, la.Tp = g.Tp, la.Hp = g.Hp, la.Wp = g.Wp, la.Cp = g.Cp;
   la.c_in = d.c_in, la.Fin = p->Fin, la.ng = p->ng, la.Klp = p->Klp;
   la.x_sB = (long long)d.t_in * d.h * d.w * d.c_in;
   la.x_sT = d.ndim == 3 ? (long long)d.h * d.w * d.c_in : 0;
+  return la;
+}
+
+// lift + L Fourier layers; leaves the last layer's output in *final_act
+static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final_act, cudaStream_t st) {
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  const LiftArgs la = make_lift_args(p, B, x, p->act[0]);
   {
     StageScope sc(&p->timing, ST_LIFT, st);
     if (p->use_tc_lift) {
@@ -569,7 +610,7 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
 }
 
 static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a, const float* aff_b, float* out,
-                    long long out_sB, float* state, cudaStream_t st) {
+                    long long out_sB, float* state, cudaStream_t st, bool allow_tc = true) {
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
   ProjArgs pa{};
@@ -584,7 +625,7 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a
   pa.st_sB = (long long)d.t_in * HW * d.c_in;
   pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
   StageScope sc(&p->timing, ST_PROJ, st);
-  if (p->use_tc_proj) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
+  if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
   return launch_proj(pa, st);
 }
 
@@ -764,6 +805,240 @@ double b200fno_algorithmic_bytes(const b200fno_plan_t* p, int32_t batch) {
   const double act = (double)d.width * g.Tp * g.Hp * g.Wp * 4;
   const double K = (d.ndim == 3 ? 4.0 * d.modes1 : 2.0) * d.modes2 * d.modes3;
   return batch * (in + out + d.n_layers * 2.0 * act) + (double)d.n_layers * d.width * d.width * K * 8.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Training path (train.py:321-334): train-mode forward + backward.  fp32 FFMA kernels throughout.
+// ---------------------------------------------------------------------------------------------
+struct TrainLayout {
+  size_t A, S, BNC, WSP, G, DH, DF, ST, total;
+};
+static TrainLayout train_layout(const b200fno_plan* p) {
+  const Geom& g = p->g;
+  const int B = p->d.max_batch, L = p->d.n_layers;
+  const size_t P = (size_t)B * g.Tp * g.Hp * g.Wp;
+  TrainLayout t;
+  t.A = align_up(g.act_elems(B), 64);
+  t.S = align_up(g.s_elems(B), 64);
+  t.BNC = align_up((size_t)6 * g.Cp, 64);
+  t.WSP = align_up((size_t)g.NM * g.Cp * 2 * g.Cp, 64);
+  t.G = align_up(P * (size_t)std::max(128, p->Klp), 64);
+  t.DH = align_up(P * 128, 64);
+  t.DF = align_up(P * (size_t)p->Fp, 64);
+  t.ST = align_up((size_t)4 * g.Cp, 64);  // 2*Cp doubles
+  t.total = (size_t)(2 * L + 3) * t.A + (size_t)L * (t.S + t.BNC) + 2 * t.WSP + t.G + t.DH + t.DF + t.ST;
+  return t;
+}
+
+size_t b200fno_train_workspace_bytes(const b200fno_plan_t* p) { return p ? train_layout(p).total * sizeof(float) : 0; }
+
+static int build_train_tables(b200fno_plan* p) {
+  if (p->tr.tbase) return 0;
+  const Geom& g = p->g;
+  Tables tmp;
+  std::vector<float> h[6];
+  B2_TRY(compute_tables_host(g, p->d.modes1, p->d.modes2, &tmp, h));
+  const int KH = g.KH, KT = g.KT, Hp = g.Hp, Tp = g.Tp, Wp = g.Wp, K2 = g.K2;
+  auto transpose = [](const std::vector<float>& src, int ld_src, int rows, int cols, int ld_dst) {
+    std::vector<float> out((size_t)cols * ld_dst, 0.f);  // out[c][r] = src[r][c]
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) out[(size_t)c * ld_dst + r] = src[(size_t)r * ld_src + c];
+    return out;
+  };
+  std::vector<float> t[6];
+  t[0] = transpose(h[5], g.K2p, Wp, K2, tmp.ldLF);            // GtT  [K2][ldLF]
+  t[1] = transpose(h[4], tmp.ldLHi, 2 * Hp, 2 * KH, tmp.ldLH);  // LHiT [2KH][ldLH]
+  t[4] = transpose(h[1], tmp.ldLH, 2 * KH, 2 * Hp, tmp.ldLHi);  // LHT  [2Hp][ldLHi]
+  t[5] = transpose(h[0], tmp.ldLF, K2, Wp, g.K2p);             // LFT  [Wp][K2p]
+  if (g.ndim == 3) {
+    t[2] = transpose(h[3], tmp.ldLTi, 2 * Tp, 2 * KT, tmp.ldLT);  // LTiT [2KT][ldLT]
+    t[3] = transpose(h[2], tmp.ldLT, 2 * KT, 2 * Tp, tmp.ldLTi);  // LTT  [2Tp][ldLTi]
+  }
+  size_t off[7] = {0};
+  for (int i = 0; i < 6; ++i) off[i + 1] = off[i] + (size_t)round_up((int)t[i].size() + 4, 64);
+  std::vector<int> slots(Tp + Hp, -1);
+  for (int s = 0; s < KT; ++s) slots[tmp.ft[s]] = s;
+  for (int s = 0; s < KH; ++s) slots[Tp + tmp.fh[s]] = s;
+  const size_t bytes = off[6] * sizeof(float) + slots.size() * sizeof(int);
+  B2_CUDA(cudaMalloc((void**)&p->tr.tbase, bytes));
+  B2_CUDA(cudaMemset(p->tr.tbase, 0, bytes));
+  for (int i = 0; i < 6; ++i)
+    if (!t[i].empty())
+      B2_CUDA(cudaMemcpy(p->tr.tbase + off[i], t[i].data(), t[i].size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->tr.GtT = p->tr.tbase + off[0], p->tr.LHiT = p->tr.tbase + off[1], p->tr.LTiT = p->tr.tbase + off[2];
+  p->tr.LTT = p->tr.tbase + off[3], p->tr.LHT = p->tr.tbase + off[4], p->tr.LFT = p->tr.tbase + off[5];
+  p->tr.slot_t = (int*)(p->tr.tbase + off[6]);
+  p->tr.slot_h = p->tr.slot_t + Tp;
+  B2_CUDA(cudaMemcpy(p->tr.slot_t, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b200fno_train_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes) {
+  if (!p || !workspace) {
+    set_error("null argument");
+    return B200FNO_EINVAL;
+  }
+  if (!p->ws) {
+    set_error("b200fno_plan_bind must be called before b200fno_train_bind");
+    return B200FNO_ESTATE;
+  }
+  const TrainLayout t = train_layout(p);
+  if (workspace_bytes < t.total * sizeof(float) || ((uintptr_t)workspace & 255)) {
+    set_error("training workspace too small (%zu < %zu) or not 256-byte aligned", workspace_bytes,
+              t.total * sizeof(float));
+    return B200FNO_EINVAL;
+  }
+  B2_TRY(build_train_tables(p));
+  const int L = p->d.n_layers;
+  float* w = (float*)workspace;
+  auto& tr = p->tr;
+  tr.xs.resize(L + 1), tr.zs.resize(L), tr.Ssave.resize(L), tr.bnc.resize(L);
+  for (int l = 0; l <= L; ++l) tr.xs[l] = w, w += t.A;
+  for (int l = 0; l < L; ++l) tr.zs[l] = w, w += t.A;
+  tr.g0 = w, w += t.A;
+  tr.g1 = w, w += t.A;
+  for (int l = 0; l < L; ++l) tr.Ssave[l] = w, w += t.S;
+  for (int l = 0; l < L; ++l) tr.bnc[l] = w, w += t.BNC;
+  tr.Wadj = w, w += t.WSP;
+  tr.dWpk = w, w += t.WSP;
+  tr.G = w, w += t.G;
+  tr.dH = w, w += t.DH;
+  tr.dF = w, w += t.DF;
+  tr.stats = (double*)w;
+  tr.bound = true, tr.fwd_done = false;
+  return 0;
+}
+
+int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, float* y, float* const* bn_running_mean,
+                          float* const* bn_running_var, float momentum, void* stream) {
+  B2_TRY(check_ready(p, batch));
+  if (!x || !y) {
+    set_error("null tensor");
+    return B200FNO_EINVAL;
+  }
+  if (!p->tr.bound) {
+    set_error("b200fno_train_bind must be called before b200fno_train_forward");
+    return B200FNO_ESTATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  auto& tr = p->tr;
+  const int B = batch, L = d.n_layers, C = d.width;
+  const long long rows = (long long)B * g.Tp * g.Hp, P = rows * g.Wp;
+  tr.fwd_done = false;
+  B2_TRY(launch_lift(make_lift_args(p, B, x, tr.xs[0]), st));
+  for (int l = 0; l < L; ++l) {
+    const LayerPacked& Lp = p->layers[l];
+    B2_TRY(run_spectral(g, p->tab, B, tr.xs[l], Lp.spec, p->bufAD, p->bufBC, tr.Ssave[l], p->bufO, st));
+    // z = conv1x1(x) + bias + irfft_W(D)   (fno.py:114-116), BatchNorm and GELU follow as separate passes
+    B2_TRY(launch_layer(tr.xs[l], tr.zs[l], Lp.convT, p->tab.Gt, p->bufAD, nullptr, Lp.cbias, rows, g.Wp, g.Cp, g.K2,
+                        g.K2p, 0, st));
+    B2_TRY(launch_colstats(tr.zs[l], P, g.Cp, tr.stats, st));
+    B2_TRY(launch_bn_finalize(tr.stats, P, d.bn_eps, Lp.gamma, Lp.beta, C, g.Cp, tr.bnc[l],
+                              bn_running_mean ? bn_running_mean[l] : nullptr,
+                              bn_running_var ? bn_running_var[l] : nullptr, momentum, st));
+    B2_TRY(launch_bn_apply(tr.zs[l], tr.xs[l + 1], P, g.Cp, tr.bnc[l], l < L - 1, st));
+  }
+  const long long out_sB = (long long)d.t_out * d.h * d.w * d.c_out;
+  B2_TRY(run_proj(p, B, tr.xs[L], nullptr, nullptr, y, out_sB, nullptr, st, /*allow_tc=*/false));
+  tr.fwd_done = true, tr.last_batch = B;
+  return 0;
+}
+
+int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, const float* dy,
+                           const b200fno_grads_t* gr, void* stream) {
+  B2_TRY(check_ready(p, batch));
+  if (!x || !dy || !gr) {
+    set_error("null argument");
+    return B200FNO_EINVAL;
+  }
+  auto& tr = p->tr;
+  if (!tr.bound || !tr.fwd_done || tr.last_batch != batch) {
+    set_error("b200fno_train_backward needs a preceding b200fno_train_forward of the same batch (%d)", batch);
+    return B200FNO_ESTATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  const int B = batch, L = d.n_layers, C = d.width, Cp = g.Cp, nf = p->Fin + p->ng;
+  const long long rows = (long long)B * g.Tp * g.Hp, P = rows * g.Wp;
+  const long long n_hw = (long long)g.m3 * Cp, n_t = (long long)g.KH * n_hw;
+  const Tables& tab = p->tab;
+  auto zero = [&](float* ptr, size_t n) -> int {
+    if (ptr) B2_CUDA(cudaMemsetAsync(ptr, 0, n * sizeof(float), st));
+    return 0;
+  };
+  B2_TRY(zero(gr->fc2_w, (size_t)p->Fout * 128));
+  B2_TRY(zero(gr->fc2_b, p->Fout));
+  B2_TRY(zero(gr->fc1_w, (size_t)128 * C));
+  B2_TRY(zero(gr->fc1_b, 128));
+  B2_TRY(zero(gr->fc0_w, (size_t)C * nf));
+  B2_TRY(zero(gr->fc0_b, C));
+  for (int l = 0; l < L; ++l) {
+    if (gr->conv_w) B2_TRY(zero(gr->conv_w[l], (size_t)C * C));
+    if (gr->conv_b) B2_TRY(zero(gr->conv_b[l], C));
+  }
+  // ---- projection backward (fno.py:121-128)
+  ProjBwdArgs pb{};
+  pb.act = tr.xs[L], pb.dy = dy, pb.fc1T = p->fc1T, pb.fc1b = p->fc1b, pb.fc2W = p->fc2W, pb.fc1W = p->fc1W;
+  pb.out_off = p->out_off, pb.G = tr.G, pb.dH = tr.dH, pb.dF = tr.dF, pb.dact = tr.g0;
+  pb.B = B, pb.T = p->Tv, pb.H = d.h, pb.W = d.w, pb.Tp = g.Tp, pb.Hp = g.Hp, pb.Wp = g.Wp, pb.Cp = Cp;
+  pb.Fout = p->Fout, pb.Fp = p->Fp, pb.c_out = d.c_out;
+  const long long HW = (long long)d.h * d.w;
+  pb.out_sB = (long long)d.t_out * HW * d.c_out;
+  pb.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
+  B2_TRY(launch_proj_bwd(pb, st));
+  if (gr->fc2_w) B2_TRY(launch_wgrad(tr.dF, p->Fp, p->Fp, p->Fout, tr.G, 128, 128, 128, P, gr->fc2_w, 128, nullptr, st));
+  if (gr->fc2_b) B2_TRY(launch_colsum(tr.dF, p->Fp, p->Fout, P, gr->fc2_b, st));
+  if (gr->fc1_w) B2_TRY(launch_wgrad(tr.dH, 128, 128, 128, tr.xs[L], Cp, Cp, C, P, gr->fc1_w, C, nullptr, st));
+  if (gr->fc1_b) B2_TRY(launch_colsum(tr.dH, 128, 128, P, gr->fc1_b, st));
+  float *gy = tr.g0, *other = tr.g1;
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerPacked& Lp = p->layers[l];
+    // GELU' (not after the last layer, fno.py:118-119) and BatchNorm backward, in place: gy becomes dz
+    B2_TRY(launch_bn_backward(gy, tr.zs[l], gy, P, C, Cp, tr.bnc[l], l < L - 1, tr.stats,
+                              gr->bn_weight ? gr->bn_weight[l] : nullptr, gr->bn_bias ? gr->bn_bias[l] : nullptr, st));
+    if (gr->conv_w && gr->conv_w[l])
+      B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.xs[l], Cp, Cp, C, P, gr->conv_w[l], C, nullptr, st));
+    if (gr->conv_b && gr->conv_b[l]) B2_TRY(launch_colsum(gy, Cp, C, P, gr->conv_b[l], st));
+    // adjoint of irfft_W, ifft_H, ifft_T: the forward kernels with transposed tables
+    B2_TRY(launch_lmul(tr.GtT, tab.ldLF, g.K2, g.Wp, gy, (long long)g.Wp * Cp, Cp, p->bufAD, (long long)g.K2 * Cp, Cp, Cp,
+                       (int)rows, st));
+    float* dO = p->bufO;
+    B2_TRY(launch_lmul(tr.LHiT, tab.ldLH, 2 * g.KH, 2 * g.Hp, p->bufAD, (long long)g.Hp * 2 * n_hw, n_hw,
+                       g.ndim == 3 ? p->bufBC : dO, 2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+    if (g.ndim == 3)
+      B2_TRY(launch_lmul(tr.LTiT, tab.ldLT, 2 * g.KT, 2 * g.Tp, p->bufBC, (long long)g.Tp * 2 * n_t, n_t, dO,
+                         2LL * g.KT * n_t, n_t, (int)n_t, B, st));
+    // spectral weights: dW = conj(S) (x) dO per mode;  dS = dO (x) conj(W)^T
+    if (gr->spec_w) {
+      B2_TRY(launch_modes_wgrad(tr.Ssave[l], dO, tr.dWpk, B, g.NM, Cp, st));
+      B2_TRY(launch_unpack_spectral_grad(tr.dWpk, gr->spec_w + (size_t)l * p->ncorner, p->ncorner, g, C, C, d.modes1,
+                                         d.modes2, tr.slot_t, tr.slot_h, st));
+    }
+    B2_TRY(launch_pack_spectral_adj(Lp.spec, tr.Wadj, g.NM, Cp, st));
+    B2_TRY(launch_modes(dO, tr.Wadj, p->bufS, B, g.NM, Cp, st));
+    // adjoint of fft_T, fft_H
+    const float* dBh = p->bufS;
+    if (g.ndim == 3) {
+      B2_TRY(launch_lmul(tr.LTT, tab.ldLTi, 2 * g.Tp, 2 * g.KT, p->bufS, 2LL * g.KT * n_t, n_t, p->bufBC,
+                         (long long)g.Tp * 2 * n_t, n_t, (int)n_t, B, st));
+      dBh = p->bufBC;
+    }
+    B2_TRY(launch_lmul(tr.LHT, tab.ldLHi, 2 * g.Hp, 2 * g.KH, dBh, 2LL * g.KH * n_hw, n_hw, p->bufAD,
+                       (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
+    // dx = dz . conv_w  +  rfft_W^T(dA): the layer kernel with the untransposed conv weight and LF^T
+    B2_TRY(launch_layer(gy, other, Lp.convW, tr.LFT, p->bufAD, nullptr, nullptr, rows, g.Wp, Cp, g.K2, g.K2p, 0, st));
+    std::swap(gy, other);
+  }
+  // ---- lift backward (fno.py:106-109): d fc0 = dx_0^T . [features | grid | 1]
+  if (gr->fc0_w) {
+    B2_TRY(launch_lift_features(make_lift_args(p, B, x, nullptr), tr.G, st));
+    // column nf of the feature matrix is the constant 1 at valid points (0 in the pad region): the bias gradient
+    B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.G, p->Klp, p->Klp, nf, P, gr->fc0_w, nf, gr->fc0_b, st));
+  }
+  return 0;
 }
 
 }  // extern "C"

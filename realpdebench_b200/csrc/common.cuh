@@ -150,4 +150,34 @@ int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int 
                     cudaStream_t st);
 int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st);  // 3xTF32 planes
 
+// ---- training path (train.cu) ----------------------------------------------------
+// train-mode BatchNorm over a flat channels-last tensor [P][Cp]; bnc = [mean|rstd|a|b|s1/n|s2/n] x Cp
+int launch_colstats(const float* x, long long P, int Cp, double* stats, cudaStream_t st);
+int launch_bn_finalize(const double* stats, long long P, float eps, const float* gamma, const float* beta, int C, int Cp,
+                       float* bnc, float* run_mean, float* run_var, float momentum, cudaStream_t st);
+int launch_bn_apply(const float* z, float* y, long long P, int Cp, const float* bnc, int gelu, cudaStream_t st);
+int launch_bn_backward(const float* gy, const float* z, float* dz, long long P, int C, int Cp, float* bnc, int gelu,
+                       double* sums, float* d_gamma, float* d_beta, cudaStream_t st);
+// out[m*ldo+n] += sum_p A[p*lda+m] B[p*ldb+n], m < Mv, n < Nv (column Nv -> extra[m]); caller zeroes out
+int launch_wgrad(const float* A, int lda, int M, int Mv, const float* B, int ldb, int N, int Nv, long long P, float* out,
+                 int ldo, float* extra, cudaStream_t st);
+int launch_colsum(const float* A, int lda, int Nv, long long P, float* out, cudaStream_t st);
+
+struct ProjBwdArgs {
+  const float* act;                          // x_L [P][Cp] (padded grid, flat)
+  const float* dy;                           // [B][t_out][H][W][c_out]
+  const float *fc1T, *fc1b, *fc2W, *fc1W;    // [Cp][128], [128], [Fp][128], [128][Cp]
+  const int* out_off;                        // [Fout]
+  float *G, *dH, *dF, *dact;                 // [P][128], [P][128], [P][Fp], [P][Cp]
+  int B, T, H, W, Tp, Hp, Wp, Cp, Fout, Fp, c_out;
+  long long out_sB, out_sT;
+};
+int launch_proj_bwd(const ProjBwdArgs& a, cudaStream_t st);
+int launch_lift_features(const LiftArgs& a, float* feat, cudaStream_t st);
+int launch_pack_spectral_adj(const float* Wpk, float* Wadj, int NM, int Cp, cudaStream_t st);
+int launch_modes_wgrad(const float* S, const float* dO, float* dW, int B, int NM, int Cp, cudaStream_t st);
+int launch_unpack_spectral_grad(const float* dWpk, float* const* corners, int ncorner, const Geom& g, int ci, int co,
+                                int m1, int m2, const int* slot_t, const int* slot_h, cudaStream_t st);
+int launch_pad2d(const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols, cudaStream_t st);
+
 }  // namespace b200fno

@@ -60,3 +60,76 @@ def aggregate_throughput(units_this_rank: float, ms_this_rank: float, dist, devi
     ms = max_over_ranks(ms_this_rank, dist, device)
     units = sum_over_ranks(units_this_rank, dist, device)
     return units / (ms * 1e-3), ms
+
+
+# ---------------------------------------------------------------------------------------------------
+# data-parallel training (SURVEY.md 8e "Training"): same batch sharding, ONE gradient all-reduce per step
+# ---------------------------------------------------------------------------------------------------
+def _real_view(t: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+class GradientAllReducer:
+    """Average parameter gradients over the ranks after ``loss.backward()`` (train.py:329), before
+    ``optimizer.step()`` (train.py:333) - what DDP would do to the reference's single-GPU step.
+
+    Gradients (complex64 spectral weights viewed as fp32 pairs) are packed into flat fp32 buckets, each bucket
+    is all-reduced asynchronously (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests) and scattered back
+    divided by the world size.  With NVSwitch the cost is launch-latency bound, not link bound, so the default
+    bucket is large (256 MB: the whole fsi FNO-2D model is one 268 MB message).
+    BatchNorm batch statistics stay per rank (the reference has no SyncBN); ``sync_buffers`` broadcasts rank 0's
+    running statistics like DDP's buffer broadcast."""
+
+    def __init__(self, module: torch.nn.Module, dist, bucket_bytes: int = 256 << 20):
+        self.module, self.dist = module, dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.buckets, cur, cur_n = [], [], 0
+        for p in self.params:
+            n = _real_view(p).numel()
+            if cur and (cur_n + n) * 4 > bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += n
+        if cur:
+            self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+
+    def sync_parameters(self, src: int = 0) -> None:
+        """Broadcast rank ``src``'s parameters and buffers (start of training / after loading a checkpoint)."""
+        if self.dist is None:
+            return
+        for t in list(self.module.parameters()) + list(self.module.buffers()):
+            self.dist.broadcast(_real_view(t.data), src=src)
+
+    def sync_buffers(self, src: int = 0) -> None:
+        if self.dist is None:
+            return
+        for t in self.module.buffers():
+            self.dist.broadcast(t.data, src=src)
+
+    @torch.no_grad()
+    def __call__(self) -> int:
+        """All-reduce + average every ``.grad``.  Returns the number of bytes reduced (0 on a single rank)."""
+        if self.dist is None or self.world == 1:
+            return 0
+        works, total = [], 0
+        for i, bucket in enumerate(self.buckets):
+            grads = [_real_view(p.grad).reshape(-1) for p in bucket]
+            n = sum(g.numel() for g in grads)
+            flat = self._flat[i]
+            if flat is None or flat.numel() != n or flat.device != grads[0].device:
+                flat = self._flat[i] = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            torch.cat(grads, out=flat)
+            works.append(self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, async_op=True))
+            total += n * 4
+        inv = 1.0 / self.world
+        for i, bucket in enumerate(self.buckets):
+            works[i].wait()
+            off = 0
+            for p in bucket:
+                g = _real_view(p.grad)
+                g.copy_(self._flat[i][off:off + g.numel()].view_as(g)).mul_(inv)
+                off += g.numel()
+        return total

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _capi
-from ._capi import Desc, Weights, check
+from ._capi import Desc, Grads, Weights, check
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -37,7 +37,7 @@ class FNOEngine:
         self._plan: Optional[C.c_void_p] = None
         self._max_batch = 0
         self._device: Optional[torch.device] = None
-        self._ws = self._packed = None
+        self._ws = self._packed = self._train_ws = None
         self._weights_key = None
         self._keepalive: List[torch.Tensor] = []
 
@@ -45,7 +45,7 @@ class FNOEngine:
     def _destroy(self):
         if self._plan is not None:
             _capi.lib().b200fno_plan_destroy(self._plan)
-        self._plan, self._ws, self._weights_key = None, None, None
+        self._plan, self._ws, self._weights_key, self._train_ws = None, None, None, None
 
     def __del__(self):  # pragma: no cover - interpreter shutdown order
         try:
@@ -159,6 +159,66 @@ class FNOEngine:
                                               state.data_ptr() if state is not None else None, out.data_ptr(),
                                               stream))
         return out
+
+    # -- training path ----------------------------------------------------------
+    def _ensure_train_ws(self, device: torch.device):
+        if self._train_ws is not None:
+            return
+        L = _capi.lib()
+        nbytes = L.b200fno_train_workspace_bytes(self._plan)
+        self._train_ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(L.b200fno_train_bind(self._plan, self._train_ws.data_ptr(), nbytes))
+
+    def train_forward(self, x: torch.Tensor, sd: dict, key, running_mean: Sequence[Optional[torch.Tensor]],
+                      running_var: Sequence[Optional[torch.Tensor]], momentum: float) -> torch.Tensor:
+        """FNO3d.forward in .train() mode (batch-statistics BatchNorm, running buffers updated in place);
+        keeps what ``train_backward`` needs inside the engine's training workspace."""
+        _require_cuda(x, "input")
+        if tuple(x.shape[1:]) != self.shape_in:
+            raise RuntimeError(f"b200fno: input shape {tuple(x.shape)} does not match [B,{self.shape_in}]")
+        x = x.contiguous()
+        stream = self.prepare(x.shape[0], x.device, sd, key)
+        self._ensure_train_ws(x.device)
+        for t in list(running_mean) + list(running_var):
+            if t is not None:
+                _require_cuda(t, "BatchNorm running statistic")
+        rm = _capi.ptr_array([t.data_ptr() for t in running_mean]) if all(t is not None for t in running_mean) else None
+        rv = _capi.ptr_array([t.data_ptr() for t in running_var]) if all(t is not None for t in running_var) else None
+        y = torch.empty((x.shape[0], *self.shape_out), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_capi.lib().b200fno_train_forward(self._plan, x.shape[0], x.data_ptr(), y.data_ptr(), rm, rv,
+                                                    float(momentum), stream))
+        return y
+
+    def train_backward(self, x: torch.Tensor, dy: torch.Tensor, params: dict) -> dict:
+        """Parameter gradients of the last ``train_forward`` in the reference layout.
+        ``params``: name -> parameter tensor (reference state_dict names); returns name -> gradient tensor."""
+        _require_cuda(dy, "output gradient")
+        x, dy = x.contiguous(), dy.contiguous()
+        ncorner = 4 if self.ndim == 3 else 2
+        grads = {k: torch.empty_like(v) for k, v in params.items()}
+
+        def ptr(name):
+            g = grads[name]
+            return (torch.view_as_real(g) if g.is_complex() else g).data_ptr()
+
+        n = self.n_layers
+        arrs = [
+            _capi.ptr_array([ptr(f"spectral_convs.{i}.weights{k + 1}") for i in range(n) for k in range(ncorner)]),
+            _capi.ptr_array([ptr(f"convs.{i}.weight") for i in range(n)]),
+            _capi.ptr_array([ptr(f"convs.{i}.bias") for i in range(n)]),
+            _capi.ptr_array([ptr(f"bns.{i}.weight") for i in range(n)]),
+            _capi.ptr_array([ptr(f"bns.{i}.bias") for i in range(n)]),
+        ]
+        g = Grads(fc0_w=ptr("fc0.weight"), fc0_b=ptr("fc0.bias"), spec_w=arrs[0], conv_w=arrs[1], conv_b=arrs[2],
+                  bn_weight=arrs[3], bn_bias=arrs[4], fc1_w=ptr("fc1.weight"), fc1_b=ptr("fc1.bias"),
+                  fc2_w=ptr("fc2.weight"), fc2_b=ptr("fc2.bias"))
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            check(_capi.lib().b200fno_train_backward(self._plan, x.shape[0], x.data_ptr(), dy.data_ptr(), C.byref(g),
+                                                     stream))
+        return grads
 
     def resolved_impl(self) -> str:
         """'tc' if the tcgen05 layer kernel is in use for this shape, else 'simt' (plan must exist)."""

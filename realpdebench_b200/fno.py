@@ -55,6 +55,41 @@ class SpectralConv2d(nn.Module):
         return spectral_conv(x, [self.weights1, self.weights2])
 
 
+class _TrainForward(torch.autograd.Function):
+    """Train-mode forward / backward on the engine (b200fno_train_forward / b200fno_train_backward).
+
+    The parameters are inputs of the Function, so autograd delivers the engine's gradients to the very
+    ``nn.Parameter`` objects ``train.py:290`` hands to Adam (and DDP-style hooks fire).  The gradient with
+    respect to the input field is not produced (the reference training loop never needs it)."""
+
+    @staticmethod
+    def forward(ctx, module, x, names, *params):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("b200fno: the training path does not produce the gradient w.r.t. the input tensor")
+        sd, key = module._engine_state()
+        bns = list(module.bns)
+        track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
+        rm = [bn.running_mean if track else None for bn in bns]
+        rv = [bn.running_var if track else None for bn in bns]
+        momentum = bns[0].momentum if bns[0].momentum is not None else 0.1
+        y = module._engine.train_forward(x, sd, key, rm, rv, momentum)
+        if track:
+            for bn in bns:
+                bn.num_batches_tracked += 1  # nn.BatchNorm bookkeeping (buffer, also in state_dict)
+            # the engine updated the running buffers in place behind torch's version counters
+            module._stats_epoch = getattr(module, "_stats_epoch", 0) + 1
+        ctx.module, ctx.names, ctx.x = module, names, x
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        need = ctx.needs_input_grad[3:]
+        grads = ctx.module._engine.train_backward(ctx.x, dy, dict(zip(ctx.names, ctx.params)))
+        out = tuple(grads[n] if nd else None for n, nd in zip(ctx.names, need))
+        return (None, None, None) + out
+
+
 class _EngineFNO(Model):
     """Shared host logic of FNO3d / FNO2d: parameter bookkeeping + engine dispatch."""
 
@@ -77,20 +112,20 @@ class _EngineFNO(Model):
         sd = {k: v for k, v in self.named_parameters()}
         for i, bn in enumerate(self.bns):
             sd[f"bns.{i}.running_mean"], sd[f"bns.{i}.running_var"] = bn.running_mean, bn.running_var
-        key = tuple((t.data_ptr(), t._version) for t in sd.values())
+        key = tuple((t.data_ptr(), t._version) for t in sd.values()) + (getattr(self, "_stats_epoch", 0),)
         return sd, key
 
     def _check_eval(self):
         if self.training:
-            raise NotImplementedError(
-                "b200fno: the CUDA engine implements the eval-mode forward (BatchNorm running statistics) and the "
-                "rollout; the training forward/backward (train.py:321-334, SURVEY.md 8f row N1) is not built yet. "
-                "Call model.eval() first.")
+            raise RuntimeError("b200fno: rollout() is the evaluation loop of eval.py; call model.eval() first")
 
     def forward(self, x):
-        self._check_eval()
         sd, key = self._engine_state()
-        return self._engine.forward(x, sd, key)
+        if not self.training:
+            return self._engine.forward(x, sd, key)
+        # train mode (train.py:325-329): batch-statistics BatchNorm; differentiable w.r.t. every parameter
+        names = [k for k, _ in self.named_parameters()]
+        return _TrainForward.apply(self, x, names, *[sd[k] for k in names])
 
     def rollout(self, x0, affine_a, affine_b, n_steps, out=None):
         """Fused eval.py:313-321 loop; see realpdebench_b200.rollout for the full per-batch protocol."""
@@ -99,7 +134,7 @@ class _EngineFNO(Model):
         return self._engine.rollout(x0, affine_a, affine_b, n_steps, sd, key, out=out)
 
     def train_loss(self, input, target):
-        pred = self.forward(input)  # fno.py:131-133
+        pred = self(input)  # fno.py:131-133
         return mse_loss(pred, target)
 
 

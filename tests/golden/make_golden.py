@@ -15,6 +15,9 @@ What is recorded (torch 2.11.0 CPU):
                  reference FNO3d + GaussianNormalizer: plain (C_in==C_out),
                  controlled (C_in = C_out+2) and RangeNormalizer cases
   spectral2d.pt  MWT sparseKernelFT2d spectral math (2-D semantics pin)
+  train3d.pt     train.py:321-334 executed on the reference FNO3d in .train() mode (loss, gradients after the
+                 first backward, losses and state_dict after 3 Adam + StepLR steps); a plain case and one with
+                 overlapping spectral corners + T_out = 2*T_in      (python tests/golden/make_golden.py train)
 """
 import os
 import sys
@@ -69,6 +72,48 @@ def run_reference_rollout(model, normalizer, input, target, n_auto, mse_loss):
     with torch.no_grad():
         exec(eval_loop_source(), ns)
     return ns["pred"], ns["target"], ns["normalized_test_loss"], ns["preds"]
+
+
+def make_train():
+    """The reference training step, train.py:321-334 (the script body, restated here line by line around the
+    unmodified reference module + torch.optim.Adam / StepLR exactly as train.py:290-292 builds them)."""
+    torch.set_num_threads(1)
+    FNO3d, _, _, _, _ = import_reference()
+    cases = {}
+    for name, ctor, bsz, clip in (
+            ("plain", (2, 3, 4, 2, 8, (4, 8, 12, 3), (4, 8, 12, 3)), 2, 0.0),
+            ("overlap_r2", (5, 3, 2, 2, 6, (2, 9, 7, 2), (4, 9, 7, 2)), 3, 0.5)):
+        torch.manual_seed(40)
+        m = FNO3d(*ctor)
+        randomize_bn(m, 41)
+        sd0 = sd_of(m)
+        torch.manual_seed(42)
+        batches = [(torch.randn(bsz, *ctor[5]), torch.randn(bsz, *ctor[6])) for _ in range(3)]
+        optimizer = torch.optim.Adam(m.parameters(), lr=1e-3)  # train.py:290
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=2, gamma=0.5)  # train.py:292
+        losses, grads0, pred0 = [], None, None
+        for it, (input, target) in enumerate(batches):
+            m.train()  # train.py:322
+            optimizer.zero_grad()  # :325
+            if it == 0:
+                with torch.no_grad():
+                    sd_keep = sd_of(m)
+                    pred0 = m(input)  # train-mode forward (updates running stats) ...
+                    m.load_state_dict(sd_keep)  # ... undone, so the recorded step starts from sd0
+            loss = m.train_loss(input, target).mean()  # :328
+            loss.backward()  # :329
+            if it == 0:
+                grads0 = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+            if clip > 0:
+                torch.nn.utils.clip_grad_norm_(m.parameters(), clip)  # :330-331
+            optimizer.step()  # :333
+            scheduler.step()  # :334
+            losses.append(loss.item())
+        print("train", name, losses)
+        cases[name] = dict(ctor=ctor, sd0=sd0, batches=batches, lr=1e-3, step_size=2, clip=clip, losses=losses,
+                           grads0=grads0, pred0=pred0, sd_final=sd_of(m))
+    torch.save(cases, os.path.join(HERE, "train3d.pt"))
+    print("train3d.pt", os.path.getsize(os.path.join(HERE, "train3d.pt")))
 
 
 def main():
@@ -167,4 +212,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        make_train()
+    else:
+        main()
+        make_train()

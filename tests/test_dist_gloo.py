@@ -63,3 +63,68 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------- data-parallel training: gradient all-reduce
+class _Params(torch.nn.Module):
+    """Parameter container with the reference FNO3d names/dtypes (complex64 spectral weights included)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self.names = [k for k in sd if O.is_param(k)]
+        self.ps = torch.nn.ParameterList([torch.nn.Parameter(sd[k].clone()) for k in self.names])
+        self.register_buffer("running", torch.zeros(3))
+
+
+def _grads_of_shard(sd, x, t, s):
+    _, g, _ = O.train_loss_and_grads(3, {k: v.clone() for k, v in sd.items()}, x, t, s)
+    return g
+
+
+def _train_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist = D.init("gloo")
+    torch.manual_seed(0)
+    s = (4, 8, 12, 3)
+    sd = O.init_state(3, (2, 3, 4), 2, 8, s, s)
+    torch.manual_seed(1)
+    x, t = torch.randn(4, *s), torch.randn(4, *s)
+    m = _Params(sd)
+    if rank == 1:  # diverged replica: sync_parameters must restore rank 0's values
+        with torch.no_grad():
+            for p in m.ps:
+                p.mul_(0.5)
+            m.running.fill_(7.0)
+    red = D.GradientAllReducer(m, dist, bucket_bytes=4096)  # small buckets: several messages, some params split off
+    red.sync_parameters(0)
+    same = all(torch.equal(p.data, sd[k]) for k, p in zip(m.names, m.ps)) and float(m.running.sum()) == 0.0
+    lo, hi = D.shard_range(4, rank, world)
+    mine = _grads_of_shard(sd, x[lo:hi], t[lo:hi], s)
+    for k, p in zip(m.names, m.ps):
+        p.grad = mine[k].clone()
+    nbytes = red()
+    both = [_grads_of_shard(sd, x[a:b], t[a:b], s) for a, b in (D.shard_range(4, r, world) for r in range(world))]
+    ok = all(torch.allclose(p.grad, (both[0][k] + both[1][k]) / 2, rtol=1e-6, atol=1e-9) for k, p in zip(m.names, m.ps))
+    dist.barrier()
+    out.put((rank, same, ok, nbytes, len(red.buckets)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_real = None
+    for rank, same, ok, nbytes, nbuckets in res:
+        assert same and ok and nbuckets > 1
+        n_real = nbytes if n_real is None else n_real
+        assert nbytes == n_real and nbytes > 0

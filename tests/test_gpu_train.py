@@ -1,0 +1,187 @@
+"""GPU parity of the training path (train.py:321-334): train-mode forward, parameter gradients and a few
+Adam steps, through the C-ABI (b200fno_train_forward / b200fno_train_backward), against the CPU oracle's
+autograd and the golden vectors recorded from the reference (tests/golden/train3d.pt).
+
+Tolerance: relative L2 <= 1e-5 per tensor (fp32, BASELINE.json north_star) for the forward and 2e-5 for
+gradients (a gradient is a sum over ~1e5..1e6 points of fp32 products accumulated in a different order).
+``convs.*.bias`` has a mathematically zero gradient (BatchNorm removes the mean): both sides hold rounding
+noise, compared with an absolute bound relative to the size of the other gradients."""
+import pytest
+import torch
+
+from oracle import fno_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 1e-5
+TOL_GRAD = 2e-5
+
+
+@pytest.fixture(scope="module")
+def R():
+    import realpdebench_b200 as R
+    from realpdebench_b200 import _capi
+    _capi.lib()
+    return R
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def build(R, ndim, ctor, sd):
+    m = (R.FNO3d if ndim == 3 else R.FNO2d)(*ctor)
+    m.load_state_dict(sd)
+    return m.to(dev())
+
+
+def check_grads(model, ref_grads, tol=TOL_GRAD):
+    scale = max(float(v.abs().max()) for k, v in ref_grads.items() if k.endswith("weight"))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        g, r = p.grad.detach().cpu(), ref_grads[k]
+        assert g.shape == r.shape and g.dtype == r.dtype, k
+        assert torch.isfinite(torch.view_as_real(g) if g.is_complex() else g).all(), k
+        if k.startswith("convs.") and k.endswith(".bias"):
+            assert float((g - r).abs().max()) < 1e-5 * max(scale, 1e-3), k
+            continue
+        e = O.rel_l2(g, r)
+        worst = max(worst, e)
+        assert e < tol, (k, e)
+    return worst
+
+
+# ---------------------------------------------------------------- golden: the reference's own training step
+@pytest.mark.parametrize("case", ["plain", "overlap_r2"])
+def test_train_step_matches_reference_golden(R, golden, case):
+    g = golden("train3d.pt")[case]
+    m = build(R, 3, g["ctor"], g["sd0"]).train()
+    x, t = (b.to(dev()) for b in g["batches"][0])
+    loss = m.train_loss(x, t).mean()  # train.py:328
+    loss.backward()
+    assert abs(loss.item() - g["losses"][0]) < 1e-5 * abs(g["losses"][0])
+    check_grads(m, g["grads0"])
+    # train-mode forward output + BatchNorm buffer updates (momentum 0.1, unbiased variance)
+    m2 = build(R, 3, g["ctor"], g["sd0"]).train()
+    with torch.no_grad():
+        y = m2(x)
+    assert O.rel_l2(y.cpu(), g["pred0"]) < TOL_FWD
+    sd_ref = {k: v.clone() for k, v in g["sd0"].items()}
+    O.fno3d_forward(sd_ref, g["batches"][0][0], g["ctor"][6], training=True)
+    sd = m2.state_dict()
+    for i in range(g["ctor"][3]):
+        assert O.rel_l2(sd[f"bns.{i}.running_mean"].cpu(), sd_ref[f"bns.{i}.running_mean"]) < 1e-5
+        assert O.rel_l2(sd[f"bns.{i}.running_var"].cpu(), sd_ref[f"bns.{i}.running_var"]) < 1e-5
+        assert int(sd[f"bns.{i}.num_batches_tracked"]) == int(g["sd0"][f"bns.{i}.num_batches_tracked"]) + 1
+
+
+@pytest.mark.parametrize("case", ["plain", "overlap_r2"])
+def test_three_adam_steps_match_reference_golden(R, golden, case):
+    """train.py:321-334 verbatim around the engine model: Adam + StepLR (+ clip_grad_norm)."""
+    g = golden("train3d.pt")[case]
+    model = build(R, 3, g["ctor"], g["sd0"])
+    optimizer = torch.optim.Adam(model.parameters(), lr=g["lr"])
+    scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=g["step_size"], gamma=0.5)
+    losses = []
+    for input, target in g["batches"]:
+        model.train()
+        optimizer.zero_grad()
+        loss = model.train_loss(input.to(dev()), target.to(dev())).mean()
+        loss.backward()
+        if g["clip"] > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), g["clip"])
+        optimizer.step()
+        scheduler.step()
+        losses.append(loss.item())
+    assert losses == pytest.approx(g["losses"], rel=2e-5)
+    sd = model.state_dict()
+    for k, v in g["sd_final"].items():
+        if v.dtype == torch.long:
+            assert int(sd[k]) == int(v), k
+            continue
+        noisy = (k.startswith("convs.") and k.endswith(".bias")) or k.endswith("running_mean")
+        # Adam divides by sqrt(v): tiny-gradient entries amplify fp32 reduction-order differences
+        assert O.rel_l2(sd[k].cpu(), v) < (5e-2 if noisy else 2e-4), k
+    # and the trained model evaluates (eval-mode forward re-packs the updated weights and running statistics)
+    model.eval()
+    with torch.no_grad():
+        y = model(g["batches"][0][0].to(dev())).cpu()
+    sdc = {k: v.cpu() for k, v in sd.items()}
+    assert O.rel_l2(y, O.fno3d_forward(sdc, g["batches"][0][0], g["ctor"][6])) < TOL_FWD
+
+
+# ---------------------------------------------------------------- oracle autograd, assorted shapes
+@pytest.mark.parametrize("ndim,ctor,batch", [
+    (3, (3, 3, 2, 3, 6, (5, 9, 7, 2), (10, 9, 7, 2)), 3),       # odd sizes, width 6 (padded to 8), r = 2, 3 layers
+    (3, (2, 4, 4, 2, 8, (10, 16, 32, 3), (10, 16, 32, 3)), 2),  # KAT-A geometry
+    (3, (2, 3, 4, 1, 8, (4, 8, 12, 5), (4, 8, 12, 3)), 2),      # controlled: C_in = C_out + 2, single layer
+    (2, (5, 6, 2, 12, (4, 20, 28, 3), (4, 20, 28, 3)), 3),      # FNO-2D
+    (2, (12, 16, 2, 64, (4, 40, 70, 3), (4, 40, 70, 3)), 2),    # FNO-2D, width 64 / modes (12,16): >64-point rows
+    (2, (9, 8, 1, 32, (2, 11, 9, 2), (3, 11, 9, 2)), 40),       # batch > 32: several batch passes in the mode kernels
+])
+def test_gradients_match_oracle_autograd(R, ndim, ctor, batch):
+    torch.manual_seed(5)
+    m = (R.FNO3d if ndim == 3 else R.FNO2d)(*ctor)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    O.randomize_bn(sd, 17)
+    m.load_state_dict(sd)
+    m = m.to(dev()).train()
+    s_in, s_out = ctor[-2], ctor[-1]
+    x, t = torch.randn(batch, *s_in), torch.randn(batch, *s_out)
+    loss_ref, grads_ref, pred_ref = O.train_loss_and_grads(ndim, sd, x, t, s_out)
+    loss = m.train_loss(x.to(dev()), t.to(dev())).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref) < 1e-5 * abs(loss_ref)
+    check_grads(m, grads_ref)
+    for i, bn in enumerate(m.bns):
+        assert O.rel_l2(bn.running_var.cpu(), sd[f"bns.{i}.running_var"]) < 1e-5
+
+
+def test_weighted_output_gradient(R):
+    """dy other than the MSE one: backward is linear in dy (sum of two weighted losses = weighted sum of grads)."""
+    torch.manual_seed(6)
+    ctor = (2, 3, 3, 2, 8, (3, 7, 9, 2), (3, 7, 9, 2))
+    m = R.FNO3d(*ctor).to(dev()).train()
+    x = torch.randn(2, *ctor[5], device=dev())
+    w1, w2 = torch.randn(2, *ctor[6], device=dev()), torch.randn(2, *ctor[6], device=dev())
+
+    def grads(w):
+        m.zero_grad()
+        (m(x) * w).sum().backward()
+        return [p.grad.clone() for p in m.parameters()]
+
+    ga, gb, gc = grads(w1), grads(w2), grads(2.0 * w1 - 0.5 * w2)
+    for a, b, c, (k, _) in zip(ga, gb, gc, m.named_parameters()):
+        if k.startswith("convs.") and k.endswith(".bias"):
+            continue
+        assert O.rel_l2(c, 2.0 * a - 0.5 * b) < 1e-4, k
+
+
+def test_train_mode_errors(R):
+    ctor = (2, 3, 3, 1, 8, (3, 7, 9, 2), (3, 7, 9, 2))
+    m = R.FNO3d(*ctor).to(dev()).train()
+    x = torch.randn(2, *ctor[5], device=dev(), requires_grad=True)
+    with pytest.raises(RuntimeError, match="input"):
+        m(x)
+    with pytest.raises(RuntimeError, match="eval"):
+        m.rollout(x.detach(), torch.ones(2, device=dev()), torch.zeros(2, device=dev()), 1)
+
+
+# ---------------------------------------------------------------- BASELINE config C3 shape (fsi, width 128)
+def test_fsi_fno2d_train_step_vs_torch_on_gpu(R):
+    """configs/fsi/fno.yaml geometry as FNO-2D (64x64, modes (16,16), width 128), batch 4: the
+    oracle functions are device-agnostic torch code, run here on the GPU in float64 (cuFFT + autograd) as the
+    checker (torch's own fp32 GPU path uses TF32 convolutions by default and is itself only ~1e-3 accurate)."""
+    torch.manual_seed(8)
+    ctor = (16, 16, 4, 128, (20, 64, 64, 3), (20, 64, 64, 3))
+    m = R.FNO2d(*ctor).to(dev()).train()
+    to64 = lambda v: v.to(torch.cdouble if v.is_complex() else torch.double) if v.is_floating_point() or v.is_complex() else v
+    sd = {k: to64(v.detach().clone()) for k, v in m.state_dict().items()}
+    x, t = torch.randn(4, *ctor[4], device=dev()), torch.randn(4, *ctor[5], device=dev())
+    loss_ref, grads_ref, _ = O.train_loss_and_grads(2, sd, x.double(), t.double(), ctor[5])
+    loss = m.train_loss(x, t).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref) < 1e-5 * abs(loss_ref)
+    ref32 = {k: v.to(torch.cfloat if v.is_complex() else torch.float).cpu() for k, v in grads_ref.items()}
+    check_grads(m, ref32, tol=5e-5)

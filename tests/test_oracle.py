@@ -100,3 +100,28 @@ def test_fno2d_is_fno3d_with_time_folded():
     y64 = O.fno2d_forward({k: (v.double() if v.is_floating_point() else v.to(torch.cdouble) if v.is_complex() else v)
                            for k, v in sd.items()}, x.double(), s_out)
     assert O.rel_l2(y, y64) < 1e-5
+
+
+# ---------------------------------------------------------------- training step (train.py:321-334)
+@pytest.mark.parametrize("case", ["plain", "overlap_r2"])
+def test_train_step_restatement_matches_reference(golden, case):
+    g = golden("train3d.pt")[case]
+    shape_out = g["ctor"][6]
+    sd = {k: v.clone() for k, v in g["sd0"].items()}
+    x, t = g["batches"][0]
+    loss, grads, pred = O.train_loss_and_grads(3, sd, x, t, shape_out)
+    assert abs(loss - g["losses"][0]) <= 1e-6 * abs(g["losses"][0])
+    assert O.rel_l2(pred, g["pred0"]) < 1e-6
+    assert set(grads) == set(g["grads0"])
+    for k, v in g["grads0"].items():
+        # convs.*.bias: BatchNorm removes the mean, the true gradient is 0 and both sides hold rounding noise
+        assert O.rel_l2(grads[k], v) < 1e-5 or (grads[k] - v).abs().max() < 1e-6, k
+    # three Adam + StepLR steps (with gradient clipping in the second case)
+    sd = {k: v.clone() for k, v in g["sd0"].items()}
+    losses = O.train_steps(3, sd, g["batches"], shape_out, g["lr"], g["clip"], g["step_size"])
+    assert losses == pytest.approx(g["losses"], rel=1e-6)
+    for k, v in g["sd_final"].items():
+        # convs.*.bias: Adam normalises the pure rounding noise of this gradient into lr-sized steps, so the
+        # reference is not reproducible there even against itself (thread count); running_mean absorbs the bias
+        noisy = (k.startswith("convs.") and k.endswith(".bias")) or k.endswith("running_mean")
+        assert O.rel_l2(sd[k], v) < (2e-2 if noisy else 1e-5), k
