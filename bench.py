@@ -232,6 +232,8 @@ def run_engine(args):
     dev = torch.device("cuda", local)
     from realpdebench_b200 import dist as D
     dist = D.init("nccl", dev)  # None when world == 1
+    all_cpus = os.sched_getaffinity(0)
+    numa = D.bind_to_gpu_numa(local)  # pinned host buffers below are first-touched on the GPU's socket
 
     wl = args.workload
     ndim, modes, L, width, s_in, s_out, B, n_auto = WORKLOADS[wl]
@@ -337,6 +339,7 @@ def run_engine(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again
         cpu_baseline = cpu_reference_sample(wl, 2, 1)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -344,7 +347,7 @@ def run_engine(args):
         line = {"metric": METRIC, "value": value, "unit": "field-points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
-                "impl": "b200fno", "engine_impl": args.engine_impl, "e2e": e2e, "gpu_launches": launches,
+                "impl": "b200fno", "engine_impl": args.engine_impl, "e2e": e2e, "host_numa_cpulist": numa, "gpu_launches": launches,
                 "clocks": clocks.summary(), "roofline": roofline, "whole_step": whole,
                 "stages_ms_per_rollout": {k: round(v["ms"], 4) for k, v in stages.items()},
                 "cpu_baseline": cpu_baseline, "normalized_loss_check": loss / e2e_steps}

@@ -560,32 +560,31 @@ int launch_lift_features(const LiftArgs& a, float* feat, cudaStream_t st) {
 // spectral weights: adjoint pack, gradient, un-pack to the reference layout
 // ---------------------------------------------------------------------------
 // Wadj[mode][o][ri][i] = conj(W)[i][o]: feeding it to modes_kernel computes dS = dO (x) conj(W)^T,
-// the adjoint of the forward mixing (real-linear in (re, im)).
+// the adjoint of the forward mixing (real-linear in (re, im)).  32x32 tiles through shared memory:
+// grid (mode, i-tile * o-tile, ri), block (32, 8); both the read and the write are 128-byte coalesced.
 __global__ void __launch_bounds__(256) pack_spectral_adj_kernel(const float* __restrict__ Wpk, float* __restrict__ Wadj,
                                                                 int Cp) {
-  extern __shared__ float tile[];  // [2][Cp][Cp+1]
+  __shared__ float tile[32][33];
+  const int nt = (Cp + 31) / 32;
+  const int i0 = (blockIdx.y / nt) * 32, o0 = (blockIdx.y % nt) * 32, ri = blockIdx.z;
   const size_t base = (size_t)blockIdx.x * Cp * 2 * Cp;
-  const int ldt = Cp + 1;
-  for (int idx = threadIdx.x; idx < Cp * 2 * Cp; idx += blockDim.x) {
-    const int o = idx % Cp, ri = (idx / Cp) & 1, i = idx / (2 * Cp);
-    tile[(ri * Cp + i) * ldt + o] = Wpk[base + idx];
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < Cp && o < Cp) ? Wpk[base + ((size_t)i * 2 + ri) * Cp + o] : 0.f;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Cp * 2 * Cp; idx += blockDim.x) {
-    const int i = idx % Cp, ri = (idx / Cp) & 1, o = idx / (2 * Cp);
-    const float v = tile[(ri * Cp + i) * ldt + o];
-    Wadj[base + idx] = ri ? -v : v;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    if (o < Cp && i < Cp) {
+      const float v = tile[threadIdx.x][r];
+      Wadj[base + ((size_t)o * 2 + ri) * Cp + i] = ri ? -v : v;
+    }
   }
 }
 
 int launch_pack_spectral_adj(const float* Wpk, float* Wadj, int NM, int Cp, cudaStream_t st) {
-  const size_t smem = (size_t)2 * Cp * (Cp + 1) * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_error("adjoint pack: width %d too large", Cp);
-    return B200FNO_EINVAL;
-  }
-  B2_CUDA(cudaFuncSetAttribute(pack_spectral_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pack_spectral_adj_kernel<<<NM, 256, smem, st>>>(Wpk, Wadj, Cp);
+  const int nt = ceil_div(Cp, 32);
+  pack_spectral_adj_kernel<<<dim3(NM, nt * nt, 2), dim3(32, 8), 0, st>>>(Wpk, Wadj, Cp);
   B2_LAUNCHED("pack_spectral_adj_kernel");
   return 0;
 }

@@ -32,6 +32,35 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None):
     return dist
 
 
+def bind_to_gpu_numa(local_rank: int) -> Optional[str]:
+    """Pin this process to the CPUs that are NUMA-local to GPU ``local_rank`` (from the PCI device's
+    ``local_cpulist`` in sysfs) so that pinned host buffers allocated afterwards are first-touched on the
+    GPU's socket and H2D copies do not cross the inter-socket link.  Returns the cpulist applied, or None when
+    the topology is not exposed (containers without sysfs PCI entries) - never raises."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.6
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception:
+        return None
+
+
 def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [start, stop) of the global batch owned by ``rank`` (remainder to the low ranks)."""
     base, rem = divmod(global_batch, world)

@@ -98,11 +98,24 @@ def test_odd_sizes_width6_r2(R, golden):
     assert O.rel_l2(y, g["y_eval"]) < TOL
 
 
-def test_train_mode_fails_loudly(R, golden):
+def test_train_mode_forward_matches_reference_golden(R, golden):
+    """Reference module in .train() mode (batch-statistics BatchNorm on the padded tensor, fno.py:111,117):
+    output and the updated running buffers, recorded from the reference (fno3d_odd.pt)."""
     g = golden("fno3d_odd.pt")
     m = make3d(R, g["ctor"], g["sd"]).train()
-    with pytest.raises(NotImplementedError):
-        m(g["x"].to(dev()))
+    with torch.no_grad():
+        y = m(g["x"].to(dev())).cpu()
+    assert O.rel_l2(y, g["y_train"]) < TOL
+    sd = m.state_dict()
+    for k, v in g["sd_after_train"].items():
+        if "running" in k:
+            assert O.rel_l2(sd[k].cpu(), v) < TOL, k
+        elif "num_batches" in k:
+            assert int(sd[k]) == int(v), k
+    # back in eval mode the refreshed running statistics are the ones folded into the layer kernel
+    with torch.no_grad():
+        y2 = m.eval()(g["x"].to(dev())).cpu()
+    assert O.rel_l2(y2, O.fno3d_forward({k: v.cpu() for k, v in sd.items()}, g["x"], g["ctor"][6])) < TOL
 
 
 def test_cylinder_config_forward(R):
