@@ -39,9 +39,9 @@ WORKLOADS = {
     "fno3d_cylinder_64x128_rollout10": (3, (4, 12, 16), 4, 64, (20, 64, 128, 3), (20, 64, 128, 3), 16, 10),
     # BASELINE.json configs[3] (C4), one sample per GPU
     "fno3d_combustion_128x128x64_rollout10": (3, (4, 16, 16), 4, 64, (64, 128, 128, 4), (64, 128, 128, 4), 1, 10),
-    # BASELINE.json configs[4] (C5) end points of the mode sweep, single forward
-    "fno2d_modes12_256x256": (2, (12, 12), 4, 64, (1, 256, 256, 3), (1, 256, 256, 3), 16, 1),
-    "fno2d_modes64_256x256": (2, (64, 64), 4, 64, (1, 256, 256, 3), (1, 256, 256, 3), 16, 1),
+    # BASELINE.json configs[4] (C5): the mode sweep 12 -> 64 at 256^2, single forward, batch 16
+    **{f"fno2d_modes{k}_256x256": (2, (k, k), 4, 64, (1, 256, 256, 3), (1, 256, 256, 3), 16, 1)
+       for k in (12, 16, 24, 32, 48, 64)},
 }
 DEFAULT_WORKLOAD = "fno2d_cylinder_256x512_rollout20"
 METRIC = "fno_rollout_field_points_per_sec"

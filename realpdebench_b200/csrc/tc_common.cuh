@@ -56,6 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // explicit shared-state-space vector accesses (keeps ptxas from falling back to generic LD/ST)
+// Explicit shared-space scalar accesses: pointers derived from the aligned dynamic-shared base lose their
+// address space (ptxas then emits generic LD.E / ST.E, which go through the address-space check).
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+}
+// volatile keeps it ordered against the (volatile) barrier / fence asm statements; no "memory" clobber, so the
+// compiler may still hoist ordinary loads (e.g. the next element's table entry) above it
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

@@ -37,7 +37,7 @@ struct FwdWArgs {
 __global__ void __launch_bounds__(FW_THREADS, 1)
     tc_fwdw_kernel(FwdWArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sX = smem;  // FW_NS stages of [x chunk | table chunk]
   __shared__ uint64_t x_full[FW_NS], x_empty[FW_NS], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;

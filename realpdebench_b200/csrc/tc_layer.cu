@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic on the __shared__ array (no integer round trip): every derived pointer keeps its address
+  // space, so plain C++ accesses below compile to LDS/STS instead of generic LD.E/ST.E
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sX = smem;
   // stages are sized to the tile (PT points), so a 104-point tile gets a 4-deep x ring where a 128-point one gets 3
   const int SUB = a.PT * 128, XS_BYTES = 2 * SUB, OS_BYTES = 2 * SUB, NSX = a.nsx;
@@ -94,10 +96,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
   int* s_ffoff = s_fchan + 64;                // [64] frame offset of feature f inside a staged box
   int* s_pbase = s_ffoff + 64;                // [c_in <= 8][128] offset of element (point p, channel c)
   if (MODE == MODE_LIFT && a.in_tma) {
-    if (tid < 64) {
+    if (tid < 64) {  // entries past the last input feature point at element 0 (the packed W0K column is zero there)
       const int fr = tid / a.c_in;
-      s_fchan[tid] = tid - fr * a.c_in;
-      s_ffoff[tid] = (a.x_sT ? 0 : fr) * a.in_IB;
+      s_fchan[tid] = tid < a.Fin ? tid - fr * a.c_in : 0;
+      s_ffoff[tid] = tid < a.Fin ? (a.x_sT ? 0 : fr) * a.in_IB : 0;
     }
     for (int i = tid; i < a.c_in * 128; i += TCL_THREADS) {
       const int c = i >> 7, pp = i & 127, e = min(pp, PT - 1) * a.c_in + c, bx = e / a.in_IB;
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
           const float* tile = reinterpret_cast<const float*>(sX + sx * XS_BYTES);
 #pragma unroll
           for (int f = 0; f < NIN; ++f)
-            if (f < a.Fin) r[f] = __float_as_uint(tile[s_pbase[s_fchan[f] * 128 + p] + s_ffoff[f]]);
+            r[f] = __float_as_uint(tile[s_pbase[s_fchan[f] * 128 + p] + s_ffoff[f]]);  // f >= Fin: table entry 0, W0K column 0
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
           return;

@@ -50,19 +50,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmState) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sX = smem;
   uint8_t* sSt = sX + TCP_NSX * TCP_XS;
   uint8_t* sW1 = sSt + TCP_ST;
-  int* s_fchan = reinterpret_cast<int*>(sSt + TCP_ST - 2048);  // [64] channel of feature f
-  int* s_ffoff = s_fchan + 64;                                  // [64] frame offset of feature f in a box
-  int* s_pbase = s_ffoff + 64;                                  // [c_out <= 3][128] offset of (point, channel)
+  int* s_pbase = reinterpret_cast<int*>(sSt + TCP_ST - 2048) + 128;  // [c_out <= 3][128] offset of (point, channel)
   uint8_t* sW2 = sW1 + TCP_W1;
-  __shared__ uint64_t x_full[TCP_NSX], x_empty[TCP_NSX], w_full, xa_full, xa_empty, acc1_full, h_full, acc2_full,
+  __shared__ uint64_t x_full[TCP_NSX], x_empty[TCP_NSX], w_full, xa_full, xa_empty, acc1_full, h_full[4], acc2_full,
       acc_free;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_b1[128], s_b2[64], s_fa[64], s_fb[64];
-  __shared__ int s_oo[64], s_so[64];
+  __shared__ float s_b1[128], s_b2[64];
+  // per output feature, one LDS.128: TMA-store epilogue {frame offset in a box, channel, affine a, affine b + b2*a};
+  // scattered-store epilogue {offset in the prediction, offset in the next input, affine a, affine b}
+  __shared__ int4 s_fpk[64];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = blockIdx.x % a.NTW, g = blockIdx.x / a.NTW;
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     for (int i = 0; i < TCP_NSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
     mbar_init(&w_full, 1);
     mbar_init(&xa_full, 128), mbar_init(&xa_empty, 1);
-    mbar_init(&acc1_full, 1), mbar_init(&h_full, TCP_EPI + 128);
+    mbar_init(&acc1_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 256);  // 2 sixteen-column chunks x 128 lanes per hidden quarter
     mbar_init(&acc2_full, 1), mbar_init(&acc_free, TCP_EPI);
     fence_barrier_init();
   }
@@ -82,17 +83,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   if (tid < 64) {
     const bool on = tid < a.Fout;
     const int ch = on ? a.chan[tid] : 0;
-    s_b2[tid] = on ? a.fc2b[tid] : 0.f;
-    s_fa[tid] = (on && a.aff_a) ? a.aff_a[ch] : 1.f;
-    s_fb[tid] = (on && a.aff_b) ? a.aff_b[ch] : 0.f;
+    const float b2 = on ? a.fc2b[tid] : 0.f;
+    const float fa = (on && a.aff_a) ? a.aff_a[ch] : 1.f, fb = (on && a.aff_b) ? a.aff_b[ch] : 0.f;
+    s_b2[tid] = b2;
     if (OUT_TMA) {  // fold the fc2 bias into the affine: (acc + b2)*a + b = acc*a + (b2*a + b)
-      s_fb[tid] = fmaf(s_b2[tid], s_fa[tid], s_fb[tid]);
       const int fr = a.ndim3 ? tid % a.o_r : tid / a.c_out;
-      s_fchan[tid] = on ? ch : 0;
-      s_ffoff[tid] = on ? fr * a.o_OB : 0;
+      s_fpk[tid] = make_int4(on ? fr * a.o_OB : 0, on ? ch : 0, __float_as_int(fa), __float_as_int(fmaf(b2, fa, fb)));
+    } else {
+      s_fpk[tid] = make_int4(on ? a.out_off[tid] : 0, on ? a.st_off[tid] : 0, __float_as_int(fa), __float_as_int(fb));
     }
-    s_oo[tid] = on ? a.out_off[tid] : 0;
-    s_so[tid] = on ? a.st_off[tid] : 0;
   }
   if (OUT_TMA)
     for (int i = tid; i < a.c_out * 128; i += TCP_THREADS) {
@@ -178,19 +177,26 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         umma_commit(&acc1_full);
       }
       __syncwarp();
-      mbar_wait(&h_full, ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
+      // GEMM-2 is issued per hidden quarter (4 K-steps) as soon as epilogue 1 has produced it, so it overlaps
+      // the rest of epilogue 1.  Its accumulator re-uses columns [0,64) of GEMM-1's: quarters 0 and 1 together
+      // guarantee that every epilogue-1 read of those columns (chunks 0-3) has completed.
+      mbar_wait(&h_full[0], ph);
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2_hi + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, ks > 0);
+      for (int Q = 0; Q < 4; ++Q) {
+        if (Q > 0) mbar_wait(&h_full[Q], ph);
+        if (Q == 0) continue;  // quarter 0 is issued together with quarter 1
+        tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_tf32_ts(T_ACC, T_H + ks * 8, d2_lo + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, 1);
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_tf32_ts(T_ACC, T_H + ks * 8, d2_hi + (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2), idesc2, 1);
-        umma_commit(&acc2_full);
+          for (int ks = (Q == 1 ? 0 : 4 * Q); ks < 4 * Q + 4; ++ks) {
+            const uint64_t o = (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2);
+            umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2_hi + o, idesc2, ks > 0);
+            umma_tf32_ts(T_ACC, T_H + ks * 8, d2_lo + o, idesc2, 1);
+            umma_tf32_ts(T_ACC, T_H + ks * 8, d2_hi + o, idesc2, 1);
+          }
+          if (Q == 3) umma_commit(&acc2_full);
+        }
+        __syncwarp();
       }
       __syncwarp();
     }
@@ -230,15 +236,26 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       // this warp's share of epilogue 1 for the same tile: hidden columns [96, 128)
       mbar_wait(&acc1_full, it & 1);
       tc_fence_after();
-      epi1_chunk(lane_addr, 96);
-      epi1_chunk(lane_addr, 112);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&h_full);
+      // round-robin over the three warps of a lane quarter (see the epilogue warps): chunks 2 and 5
+#pragma unroll
+      for (int chunk = 2; chunk < 8; chunk += 3) {
+        epi1_chunk(lane_addr, chunk * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&h_full[chunk >> 1]);
+      }
     }
   } else if (warp >= 8) {
     const int q = warp & 3, hh = (warp - 8) >> 2, p = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // staging offset of (this thread's point, channel c): fixed for the whole kernel, kept in registers
+    int pb0 = 0, pb1 = 0, pb2 = 0;
+    if (OUT_TMA) {
+      const uint32_t a_pbase = smem_u32(s_pbase);  // byte addresses inside the staging tile
+      pb0 = (int)smem_u32(sSt) + 4 * (int)lds32(a_pbase + 4 * p);
+      if (a.c_out > 1) pb1 = (int)smem_u32(sSt) + 4 * (int)lds32(a_pbase + 4 * (128 + p));
+      if (a.c_out > 2) pb2 = (int)smem_u32(sSt) + 4 * (int)lds32(a_pbase + 4 * (256 + p));
+    }
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ph = it & 1;
       const int row = a.rows - 1 - (g + it * a.G);
@@ -247,11 +264,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       // ---- epilogue 1: hidden = GELU(acc + b1) -> TMEM as the A operand of GEMM-2 (hi | lo)
       mbar_wait(&acc1_full, ph);
       tc_fence_after();
+      // sixteen-column chunks in increasing order across the three warps of a lane quarter (hh = 0: 0,3,6;
+      // hh = 1: 1,4,7; split warp: 2,5): low hidden quarters complete first and GEMM-2 starts on them early
 #pragma unroll
-      for (int chunk = 0; chunk < 3; ++chunk) epi1_chunk(lane_addr, hh * 48 + chunk * 16);  // columns [0,48) / [48,96)
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&h_full);
+      for (int chunk = hh; chunk < 8; chunk += 3) {
+        epi1_chunk(lane_addr, chunk * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&h_full[chunk >> 1]);
+      }
       // ---- epilogue 2: + b2, rollout affine, scatter to the prediction slice and the next model input
       mbar_wait(&acc2_full, ph);
       tc_fence_after();
@@ -267,13 +288,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         const int etid = tid - 256;
         if (etid == 0) tma_store_wait_read<0>();  // the previous tile's stores have read the staging buffer
         tcp_named_bar(1, TCP_EPI);
-        float* stage = reinterpret_cast<float*>(sSt);
         if (have && p < PT) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int f = hh * 32 + i;
-            if (f < a.Fout)
-              stage[s_pbase[s_fchan[f] * 128 + p] + s_ffoff[f]] = fmaf(__uint_as_float(v[i]), s_fa[f], s_fb[f]);
+            if (f < a.Fout) {
+              const int4 k = s_fpk[f];  // warp-uniform address: one broadcast LDS.128 per feature
+              const int base = k.y == 0 ? pb0 : (k.y == 1 ? pb1 : pb2);
+              sts32((uint32_t)(base + 4 * k.x), fmaf(__uint_as_float(v[i]), __int_as_float(k.z), __int_as_float(k.w)));
+            }
           }
         }
         fence_proxy_async_smem();
@@ -294,9 +317,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         for (int i = 0; i < 32; ++i) {
           const int f = hh * 32 + i;
           if (f < a.Fout) {
-            const float y = fmaf(__uint_as_float(v[i]) + s_b2[f], s_fa[f], s_fb[f]);
-            a.out[po + s_oo[f]] = y;
-            if (a.state) a.state[ps + s_so[f]] = y;
+            const int4 k = s_fpk[f];
+            const float y = fmaf(__uint_as_float(v[i]) + s_b2[f], __int_as_float(k.z), __int_as_float(k.w));
+            a.out[po + k.x] = y;
+            if (a.state) a.state[ps + k.y] = y;
           }
         }
       }

@@ -38,7 +38,7 @@ __device__ __forceinline__ int round_up_dev(int x, int m) { return (x + m - 1) /
 __global__ void __launch_bounds__(TM_THREADS, 1)
     tc_tmul_kernel(TmulArgs a, const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmL) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   __shared__ uint64_t x_full[4], x_empty[4], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

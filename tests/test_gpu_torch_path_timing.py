@@ -58,7 +58,7 @@ def test_engine_beats_torch_cufft_path_on_c2():
         ms_eng = _time(lambda: m.rollout(x0, a, b, n_auto), 5) / n_auto
         # same results (the torch path with fp32 convolutions is the oracle itself, on another device)
         torch.backends.cudnn.allow_tf32 = False
-        pred_t = O.rollout(lambda t: O.fno2d_forward(sd_dev, t, s), norm, x, tgt, 1)[3][1]
+        pred_t = O.rollout(lambda t: O.fno2d_forward(sd_dev, t, s), norm, x, tgt[:, :s[0]], 1)[3][1]
         pred_e = m.rollout(x0, a, b, 1)
         err = O.rel_l2(pred_e, pred_t)
     res.update(engine_ms_per_step=ms_eng, batch=B, workload="fno2d_cylinder_256x512 (C2), per autoregressive step",
