@@ -38,7 +38,8 @@ def config(wl, B, world):
     return {"workload": wl, "operator": f"fno{ndim}d", "modes": list(modes), "width": width, "n_layers": L,
             "shape_in": list(s_in), "shape_out": list(s_out), "batch_per_gpu": B, "global_batch": B * world,
             "optimizer": "torch.optim.Adam(lr=1e-3) as train.py:290", "parallelism":
-            f"batch-sharded x{world}, one gradient all-reduce per step (realpdebench_b200.dist.GradientAllReducer)"}
+            f"batch-sharded x{world}, gradient all-reduce per step overlapped with the backward pass "
+            "(realpdebench_b200.dist.OverlappedGradientReducer)"}
 
 
 def run_reference(args):
@@ -88,7 +89,10 @@ def run_engine(args):
     model.load_state_dict(sd)
     model = model.to(dev).train()
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)  # train.py:290
-    reducer = D.GradientAllReducer(model, dist)
+    # N > 1: the all-reduce runs under the backward pass (events recorded by b200fno_train_backward); --no-overlap
+    # falls back to one bucketed all-reduce after loss.backward()
+    overlap = dist is not None and not args.no_overlap
+    reducer = D.OverlappedGradientReducer(model, dist) if overlap else D.GradientAllReducer(model, dist)
     reducer.sync_parameters(0)
     torch.manual_seed(1234 + rank)
     x, t = torch.randn(B, *s_in, device=dev), torch.randn(B, *s_out, device=dev)
@@ -106,7 +110,7 @@ def run_engine(args):
         loss.backward()
         if timed:
             ev["bwd"][1].record(), ev["allreduce"][0].record()
-        nbytes = reducer()
+        nbytes = reducer.bytes_last if overlap else reducer()
         if timed:
             ev["allreduce"][1].record(), ev["adam"][0].record()
         optimizer.step()
@@ -156,7 +160,7 @@ def run_engine(args):
             "e2e": {"value": world * pts / (e2e_ms * 1e-3), "unit": "field-points/s",
                     "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks.summary(), "phases_ms": phases,
-            "allreduce_bytes_per_step": nbytes, "loss": float(loss)}), flush=True)
+            "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap, "loss": float(loss.detach())}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -169,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="b200fno", choices=["b200fno", "reference"])
     ap.add_argument("--workload", default="fno2d_fsi_64x64_train", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of under it")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the bounded CPU sample (--impl reference)")
     args = ap.parse_args()
     (run_reference if args.impl == "reference" else run_engine)(args)

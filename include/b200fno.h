@@ -192,9 +192,15 @@ int b200fno_train_forward(b200fno_plan_t* plan, int32_t batch, const float* x, f
 /* Backward of the last b200fno_train_forward (autograd of fno.py:105-129 as
  * driven by loss.backward(), train.py:329): dy = dL/dy [batch][t_out][h][w][c_out]
  * -> parameter gradients.  The gradient w.r.t. the input x is not produced
- * (train.py never needs it). */
+ * (train.py never needs it).
+ * grads_ready: NULL, or n_layers+1 cudaEvent_t handles (as void*, entries may be
+ * NULL) recorded on `stream` as soon as a group of gradients is final - entry
+ * n_layers: fc1/fc2; entry l: spec_w, conv_*, bn_* of layer l (recorded from the
+ * last layer to the first); fc0 is final when the call's work completes.  A
+ * data-parallel caller waits on them from a second stream to overlap the
+ * gradient all-reduce with the rest of the backward pass. */
 int b200fno_train_backward(b200fno_plan_t* plan, int32_t batch, const float* x, const float* dy,
-                           const b200fno_grads_t* grads, void* stream);
+                           const b200fno_grads_t* grads, void* const* grads_ready, void* stream);
 
 /* ---- introspection used by bench.py / tests ------------------------------ */
 /* Kernels launched by this library on this thread since the last reset. */

@@ -112,7 +112,7 @@ def lib() -> C.CDLL:
     L.b200fno_train_forward.restype = C.c_int
     L.b200fno_train_forward.argtypes = [vp, i32, vp, vp, _fpp, _fpp, C.c_float, vp]
     L.b200fno_train_backward.restype = C.c_int
-    L.b200fno_train_backward.argtypes = [vp, i32, vp, vp, C.POINTER(Grads), vp]
+    L.b200fno_train_backward.argtypes = [vp, i32, vp, vp, C.POINTER(Grads), _fpp, vp]
     L.b200fno_algorithmic_bytes.restype = C.c_double
     L.b200fno_algorithmic_bytes.argtypes = [vp, i32]
     if L.b200fno_abi_version() != ABI_VERSION:

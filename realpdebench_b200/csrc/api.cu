@@ -947,7 +947,7 @@ int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, floa
 }
 
 int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, const float* dy,
-                           const b200fno_grads_t* gr, void* stream) {
+                           const b200fno_grads_t* gr, void* const* grads_ready, void* stream) {
   B2_TRY(check_ready(p, batch));
   if (!x || !dy || !gr) {
     set_error("null argument");
@@ -993,6 +993,13 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   if (gr->fc2_b) B2_TRY(launch_colsum(tr.dF, p->Fp, p->Fout, P, gr->fc2_b, st));
   if (gr->fc1_w) B2_TRY(launch_wgrad(tr.dH, 128, 128, 128, tr.xs[L], Cp, Cp, C, P, gr->fc1_w, C, nullptr, st));
   if (gr->fc1_b) B2_TRY(launch_colsum(tr.dH, 128, 128, P, gr->fc1_b, st));
+  // grads_ready[i]: caller's cudaEvent_t recorded as soon as the gradients of group i are final, so that a
+  // data-parallel caller can start their all-reduce on another stream under the rest of the backward pass
+  auto ready = [&](int i) -> int {
+    if (grads_ready && grads_ready[i]) B2_CUDA(cudaEventRecord((cudaEvent_t)grads_ready[i], st));
+    return 0;
+  };
+  B2_TRY(ready(L));  // fc1, fc2
   float *gy = tr.g0, *other = tr.g1;
   for (int l = L - 1; l >= 0; --l) {
     const LayerPacked& Lp = p->layers[l];
@@ -1017,6 +1024,7 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
       B2_TRY(launch_unpack_spectral_grad(tr.dWpk, gr->spec_w + (size_t)l * p->ncorner, p->ncorner, g, C, C, d.modes1,
                                          d.modes2, tr.slot_t, tr.slot_h, st));
     }
+    B2_TRY(ready(l));  // spectral, conv and BatchNorm gradients of layer l
     B2_TRY(launch_pack_spectral_adj(Lp.spec, tr.Wadj, g.NM, Cp, st));
     B2_TRY(launch_modes(dO, tr.Wadj, p->bufS, B, g.NM, Cp, st));
     // adjoint of fft_T, fft_H

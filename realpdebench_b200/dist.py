@@ -162,3 +162,83 @@ class GradientAllReducer:
                 g.copy_(self._flat[i][off:off + g.numel()].view_as(g)).mul_(inv)
                 off += g.numel()
         return total
+
+
+class OverlappedGradientReducer:
+    """Gradient averaging overlapped with the backward pass (GPU / NCCL only).
+
+    ``b200fno_train_backward`` records a CUDA event as soon as each group of gradients is final (projection first,
+    then the Fourier layers from last to first).  This object is attached to the module; the engine's autograd
+    function calls :meth:`backward_and_reduce`, which enqueues the whole backward on the compute stream, then issues
+    the all-reduce of every group on a side stream gated by that group's event - so NCCL moves layer ``l``'s 67-134 MB
+    of spectral-weight gradients over NVLink while the kernels of layers ``l-1 .. 0`` are still running - and finally
+    makes the compute stream wait for the reductions.  The gradients autograd hands to ``.grad`` are already averaged:
+    ``train.py:329-333`` needs no extra call (``ReduceOp.AVG``, no flatten copies for the large tensors)."""
+
+    def __init__(self, module: torch.nn.Module, dist):
+        self.module, self.dist = module, dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.n_layers = module.n_layers
+        dev = next(module.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("OverlappedGradientReducer needs the module on a CUDA device (use GradientAllReducer)")
+        self.side = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in range(self.n_layers + 1)]
+        for e in self.events:  # torch creates the underlying cudaEvent_t lazily on the first record
+            e.record(torch.cuda.current_stream(dev))
+        self.bytes_last = 0
+        module._grad_sync = self if self.world > 1 else None
+
+    def detach(self) -> None:
+        self.module._grad_sync = None
+
+    def sync_parameters(self, src: int = 0) -> None:
+        if self.dist is None:
+            return
+        for t in list(self.module.parameters()) + list(self.module.buffers()):
+            self.dist.broadcast(_real_view(t.data), src=src)
+
+    def _group(self, names, idx):
+        L = self.n_layers
+        if idx == L:
+            return [n for n in names if n.startswith(("fc1.", "fc2."))]
+        tag = f".{idx}."
+        return [n for n in names if tag in n and n.startswith(("spectral_convs.", "convs.", "bns."))]
+
+    def backward_and_reduce(self, engine, x, dy, params: dict) -> dict:
+        dist, L = self.dist, self.n_layers
+        cur = torch.cuda.current_stream(x.device)
+        grads = engine.train_backward(x, dy, params, ready_events=[e.cuda_event for e in self.events])
+        done = torch.cuda.Event()
+        done.record(cur)  # fc0 gradients (and everything else) final
+        works, total = [], 0
+        op = dist.ReduceOp.AVG
+        with torch.cuda.stream(self.side):
+            for idx in [L] + list(range(L - 1, -1, -1)) + [-1]:
+                self.side.wait_event(self.events[idx] if idx >= 0 else done)
+                names = self._group(grads.keys(), idx) if idx >= 0 else [n for n in grads if n.startswith("fc0.")]
+                small = [grads[n] for n in names if grads[n].numel() < (1 << 16)]
+                for n in names:
+                    g = grads[n]
+                    if g.numel() >= (1 << 16):  # spectral weights: reduced in place, no flatten copy
+                        works.append((dist.all_reduce(_real_view(g), op=op, async_op=True), None, None))
+                        total += _real_view(g).numel() * 4
+                if small:  # biases, BatchNorm affine, 1x1 conv: one coalesced message per group
+                    flat = torch.cat([_real_view(g).reshape(-1) for g in small])
+                    works.append((dist.all_reduce(flat, op=op, async_op=True), flat, small))
+                    total += flat.numel() * 4
+            for w, flat, small in works:
+                w.wait()  # the side stream waits for NCCL
+                if flat is not None:
+                    off = 0
+                    for g in small:
+                        v = _real_view(g)
+                        v.copy_(flat[off:off + v.numel()].view_as(v))
+                        off += v.numel()
+            fin = torch.cuda.Event()
+            fin.record(self.side)
+        cur.wait_event(fin)  # gradients returned to autograd are averaged as far as stream order goes
+        for g in grads.values():
+            g.record_stream(self.side)
+        self.bytes_last = total
+        return grads

@@ -191,9 +191,12 @@ class FNOEngine:
                                                     float(momentum), stream))
         return y
 
-    def train_backward(self, x: torch.Tensor, dy: torch.Tensor, params: dict) -> dict:
+    def train_backward(self, x: torch.Tensor, dy: torch.Tensor, params: dict,
+                       ready_events: Optional[Sequence[int]] = None) -> dict:
         """Parameter gradients of the last ``train_forward`` in the reference layout.
-        ``params``: name -> parameter tensor (reference state_dict names); returns name -> gradient tensor."""
+        ``params``: name -> parameter tensor (reference state_dict names); returns name -> gradient tensor.
+        ``ready_events``: optional ``n_layers + 1`` raw ``cudaEvent_t`` handles recorded when each gradient group
+        is final (see ``b200fno_train_backward``)."""
         _require_cuda(dy, "output gradient")
         x, dy = x.contiguous(), dy.contiguous()
         ncorner = 4 if self.ndim == 3 else 2
@@ -216,8 +219,9 @@ class FNOEngine:
                   fc2_w=ptr("fc2.weight"), fc2_b=ptr("fc2.bias"))
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
+            ev = _capi.ptr_array(list(ready_events)) if ready_events is not None else None
             check(_capi.lib().b200fno_train_backward(self._plan, x.shape[0], x.data_ptr(), dy.data_ptr(), C.byref(g),
-                                                     stream))
+                                                     ev, stream))
         return grads
 
     def resolved_impl(self) -> str:

@@ -85,7 +85,12 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         need = ctx.needs_input_grad[3:]
-        grads = ctx.module._engine.train_backward(ctx.x, dy, dict(zip(ctx.names, ctx.params)))
+        params = dict(zip(ctx.names, ctx.params))
+        sync = getattr(ctx.module, "_grad_sync", None)  # dist.OverlappedGradientReducer: all-reduce under the backward
+        if sync is not None:
+            grads = sync.backward_and_reduce(ctx.module._engine, ctx.x, dy, params)
+        else:
+            grads = ctx.module._engine.train_backward(ctx.x, dy, params)
         out = tuple(grads[n] if nd else None for n, nd in zip(ctx.names, need))
         return (None, None, None) + out
 
