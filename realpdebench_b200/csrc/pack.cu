@@ -16,38 +16,44 @@ struct Corners {
 // weights1 (low t, low h), weights2 (high t, low h), weights3 (low t, high h),
 // weights4 (high t, high h); where corners overlap the later assignment wins,
 // i.e. "high" beats "low" on each axis.
-__global__ void pack_spectral_kernel(Corners c, float* __restrict__ Wpk, int ndim, int Tp, int Hp, int m1, int m2,
-                                     int m3, int KT, int KH, int ci, int co, int Cp, const int* __restrict__ ft,
-                                     const int* __restrict__ fh) {
-  const size_t total = (size_t)KT * KH * m3 * Cp * 2 * Cp;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    int o = (int)(idx % Cp);
-    size_t r = idx / Cp;
-    int ri = (int)(r & 1);
-    r >>= 1;
-    int i = (int)(r % Cp);
-    r /= Cp;
-    int kw = (int)(r % m3);
-    r /= m3;
-    int khs = (int)(r % KH);
-    int kts = (int)(r / KH);
-    float v = 0.f;
-    if (i < ci && o < co) {
-      const int fH = fh[khs];
-      const bool h_hi = fH >= Hp - m2;
-      const int y = h_hi ? fH - (Hp - m2) : fH;
-      if (ndim == 3) {
-        const int fT = ft[kts];
-        const bool t_hi = fT >= Tp - m1;
-        const int x = t_hi ? fT - (Tp - m1) : fT;
-        const float* src = c.w[(h_hi ? 2 : 0) + (t_hi ? 1 : 0)];
-        v = src[(((((size_t)i * co + o) * m1 + x) * m2 + y) * m3 + kw) * 2 + ri];
-      } else {
-        const float* src = c.w[h_hi ? 1 : 0];
-        v = src[((((size_t)i * co + o) * m2 + y) * m3 + kw) * 2 + ri];
-      }
+// One CTA per (kept (T,H) frequency slot, input channel i): the source rows src[i][o][x][y][0..m3)[re,im] are
+// 2*m3 contiguous floats per output channel o, the destination rows Wpk[mode(kw)][i][ri][0..Cp) are contiguous in o:
+// transposed through shared memory so that both sides are coalesced (this runs after every optimiser step).
+__global__ void __launch_bounds__(256) pack_spectral_kernel(Corners c, float* __restrict__ Wpk, int ndim, int Tp, int Hp,
+                                                            int m1, int m2, int m3, int KH, int ci, int co, int Cp,
+                                                            const int* __restrict__ ft, const int* __restrict__ fh) {
+  extern __shared__ float tile[];  // [Cp][2*m3 + 1]
+  const int slot = blockIdx.x, i = blockIdx.y;
+  const int khs = slot % KH, kts = slot / KH;
+  const int W2 = 2 * m3, ldt = W2 + 1;
+  const int fH = fh[khs];
+  const bool h_hi = fH >= Hp - m2;
+  const int y = h_hi ? fH - (Hp - m2) : fH;
+  const float* src = nullptr;
+  size_t row_stride = 0, base = 0;  // element (o, kw, ri) at src[base + o*row_stride + kw*2 + ri]
+  if (i < ci) {
+    if (ndim == 3) {
+      const int fT = ft[kts];
+      const bool t_hi = fT >= Tp - m1;
+      const int x = t_hi ? fT - (Tp - m1) : fT;
+      src = c.w[(h_hi ? 2 : 0) + (t_hi ? 1 : 0)];
+      row_stride = (size_t)m1 * m2 * m3 * 2;
+      base = ((size_t)i * co * m1 * m2 + (size_t)x * m2 + y) * m3 * 2;
+    } else {
+      src = c.w[h_hi ? 1 : 0];
+      row_stride = (size_t)m2 * m3 * 2;
+      base = ((size_t)i * co * m2 + y) * m3 * 2;
     }
-    Wpk[idx] = v;
+  }
+  for (int idx = threadIdx.x; idx < Cp * W2; idx += blockDim.x) {
+    const int o = idx / W2, k = idx % W2;
+    tile[o * ldt + k] = (src && o < co) ? src[base + (size_t)o * row_stride + k] : 0.f;
+  }
+  __syncthreads();
+  const size_t mode0 = (size_t)slot * m3;
+  for (int idx = threadIdx.x; idx < W2 * Cp; idx += blockDim.x) {
+    const int o = idx % Cp, k = idx / Cp, kw = k >> 1, ri = k & 1;
+    Wpk[(((mode0 + kw) * Cp + i) * 2 + ri) * Cp + o] = tile[o * ldt + k];
   }
 }
 
@@ -55,10 +61,14 @@ int launch_pack_spectral(const float* const* corners, int ncorner, float* Wpk, c
                          int m2, const int* d_ft, const int* d_fh, cudaStream_t st) {
   Corners c{};
   for (int i = 0; i < ncorner; ++i) c.w[i] = corners[i];
-  size_t total = (size_t)g.NM * g.Cp * 2 * g.Cp;
-  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
-  pack_spectral_kernel<<<blocks, 256, 0, st>>>(c, Wpk, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KT, g.KH, ci, co, g.Cp,
-                                               d_ft, d_fh);
+  const size_t smem = (size_t)g.Cp * (2 * g.m3 + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("spectral pack: width %d x modes3 %d too large", g.Cp, g.m3);
+    return B200FNO_EINVAL;
+  }
+  B2_CUDA(cudaFuncSetAttribute(pack_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pack_spectral_kernel<<<dim3(g.KT * g.KH, g.Cp), 256, smem, st>>>(c, Wpk, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KH, ci, co,
+                                                                   g.Cp, d_ft, d_fh);
   B2_LAUNCHED("pack_spectral_kernel");
   return 0;
 }

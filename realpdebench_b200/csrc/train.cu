@@ -655,42 +655,47 @@ __global__ void __launch_bounds__(256) unpack_spectral_grad_kernel(const float* 
                                                                    int m3, int KH, int ci, int co, int Cp,
                                                                    const int* __restrict__ slot_t,
                                                                    const int* __restrict__ slot_h) {
+  // one CTA per (input channel i, corner element (x, y)): rows dWpk[mode(kw)][i][ri][0..co) in, rows
+  // g[i][o][x][y][0..m3)[re,im] out, transposed through shared memory (both sides coalesced)
+  extern __shared__ float tile[];  // [2*m3][co + 1]
   const int mm1 = ndim == 3 ? m1 : 1;
-  const size_t total = (size_t)ci * co * mm1 * m2 * m3 * 2;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int ri = (int)(idx & 1);
-    size_t r = idx >> 1;
-    const int kw = (int)(r % m3);
-    r /= m3;
-    const int y = (int)(r % m2);
-    r /= m2;
-    const int x = (int)(r % mm1);
-    r /= mm1;
-    const int o = (int)(r % co), i = (int)(r / co);
-    const bool h_hi = ndim == 3 ? (corner >= 2) : (corner == 1);
-    const bool t_hi = ndim == 3 ? (corner & 1) : false;
-    const int fH = h_hi ? Hp - m2 + y : y;
-    const int fT = ndim == 3 ? (t_hi ? Tp - m1 + x : x) : 0;
-    float v = 0.f;
-    // winner rule of pack_spectral_kernel: "high" owns every frequency >= N - m
-    const bool own_h = (fH >= Hp - m2) == h_hi;
-    const bool own_t = ndim == 3 ? ((fT >= Tp - m1) == t_hi) : true;
-    if (own_h && own_t) {
-      const int mode = ((ndim == 3 ? slot_t[fT] : 0) * KH + slot_h[fH]) * m3 + kw;
-      v = dWpk[(((size_t)mode * Cp + i) * 2 + ri) * Cp + o];
+  const int i = blockIdx.y, y = blockIdx.x % m2, x = blockIdx.x / m2;
+  const int W2 = 2 * m3, ldt = co + 1;
+  const bool h_hi = ndim == 3 ? (corner >= 2) : (corner == 1);
+  const bool t_hi = ndim == 3 ? (corner & 1) : false;
+  const int fH = h_hi ? Hp - m2 + y : y;
+  const int fT = ndim == 3 ? (t_hi ? Tp - m1 + x : x) : 0;
+  // winner rule of pack_spectral_kernel: "high" owns every frequency >= N - m
+  const bool own = ((fH >= Hp - m2) == h_hi) && (ndim == 3 ? ((fT >= Tp - m1) == t_hi) : true);
+  if (own) {
+    const size_t mode0 = ((size_t)(ndim == 3 ? slot_t[fT] : 0) * KH + slot_h[fH]) * m3;
+    for (int idx = threadIdx.x; idx < W2 * co; idx += blockDim.x) {
+      const int o = idx % co, k = idx / co, kw = k >> 1, ri = k & 1;
+      tile[k * ldt + o] = dWpk[(((mode0 + kw) * Cp + i) * 2 + ri) * Cp + o];
     }
-    g[idx] = v;
+  }
+  __syncthreads();
+  const size_t row_stride = (size_t)mm1 * m2 * m3 * 2;
+  const size_t base = ((size_t)i * co * mm1 * m2 + (size_t)x * m2 + y) * m3 * 2;
+  for (int idx = threadIdx.x; idx < co * W2; idx += blockDim.x) {
+    const int o = idx / W2, k = idx % W2;
+    g[base + (size_t)o * row_stride + k] = own ? tile[k * ldt + o] : 0.f;
   }
 }
 
 int launch_unpack_spectral_grad(const float* dWpk, float* const* corners, int ncorner, const Geom& g, int ci, int co,
                                 int m1, int m2, const int* slot_t, const int* slot_h, cudaStream_t st) {
-  const size_t total = (size_t)ci * co * (g.ndim == 3 ? m1 : 1) * m2 * g.m3 * 2;
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)148 * 32));
+  const size_t smem = (size_t)2 * g.m3 * (co + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("spectral gradient unpack: width %d x modes3 %d too large", co, g.m3);
+    return B200FNO_EINVAL;
+  }
+  B2_CUDA(cudaFuncSetAttribute(unpack_spectral_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((g.ndim == 3 ? m1 : 1) * m2, ci);
   for (int c = 0; c < ncorner; ++c) {
     if (!corners[c]) continue;
-    unpack_spectral_grad_kernel<<<blocks, 256, 0, st>>>(dWpk, corners[c], c, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KH, ci,
-                                                        co, g.Cp, slot_t, slot_h);
+    unpack_spectral_grad_kernel<<<grid, 256, smem, st>>>(dWpk, corners[c], c, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KH, ci,
+                                                         co, g.Cp, slot_t, slot_h);
     B2_LAUNCHED("unpack_spectral_grad_kernel");
   }
   return 0;
