@@ -1,5 +1,6 @@
 // Plan object and the extern "C" entry points declared in include/b200fno.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -44,6 +45,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int64_t& launch_counter() { return g_launches; }
+static thread_local bool g_pdl = false;
+bool& pdl_enabled() { return g_pdl; }
 
 }  // namespace b200fno
 
@@ -119,6 +122,7 @@ struct b200fno_plan {
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
   std::vector<LayerPacked> layers;
   // tensor-core path
+  bool use_pdl = true;  // B200FNO_NO_PDL=1 in the environment disables it (A/B measurements)
   bool use_tc = false, use_tc_lift = false;
   CUtensorMap tmAct[2], tmD, tmW0;
   float* W0K = nullptr;  // [2][64][64] lift weights as K-major hi|lo planes
@@ -298,6 +302,7 @@ int b200fno_plan_create(const b200fno_desc_t* d, b200fno_plan_t** out) {
     return B200FNO_EINVAL;
   }
   p->d = *d;
+  p->use_pdl = getenv("B200FNO_NO_PDL") == nullptr;
   cudaGetDevice(&p->device);
   const int pad = d->padding;
   int rc = make_geom(d->ndim, d->t_in + pad, d->h + pad, d->w + pad, d->width, d->modes1, d->modes2, d->modes3, &p->g);
@@ -577,6 +582,15 @@ static LiftArgs make_lift_args(const b200fno_plan* p, int B, const float* x, flo
 static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final_act, cudaStream_t st) {
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
+  // the whole trunk is chained with programmatic dependent launches (common.cuh); per-stage event timing sits
+  // between the launches and would break the chain, so it keeps plain launches.  The lift may overlap the tail of
+  // whatever kernel precedes it (projection of the previous rollout step, a weight-pack or a torch kernel): before
+  // its pdl_wait() it only touches plan constants.
+  struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
+    ~PdlScope() { pdl_enabled() = prev; }
+  } pdl_scope(p->use_pdl && !p->timing.enabled);
   const LiftArgs la = make_lift_args(p, B, x, p->act[0]);
   {
     StageScope sc(&p->timing, ST_LIFT, st);
@@ -625,6 +639,12 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a
   pa.st_sB = (long long)d.t_in * HW * d.c_in;
   pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
   StageScope sc(&p->timing, ST_PROJ, st);
+  const bool prev_pdl = pdl_enabled();
+  pdl_enabled() = p->use_pdl && !p->timing.enabled && allow_tc;  // follows the last layer kernel of run_trunk
+  struct Restore {
+    bool v;
+    ~Restore() { pdl_enabled() = v; }
+  } restore{prev_pdl};
   if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
   return launch_proj(pa, st);
 }

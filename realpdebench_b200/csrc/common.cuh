@@ -42,6 +42,30 @@ int64_t& launch_counter();
     if (_r != 0) return _r;   \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------
+// Inside b200fno_forward / b200fno_rollout every kernel after the lift is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident, set up barriers / TMEM /
+// tensor-map prefetches while the previous kernel drains, and block in pdl_wait() until that kernel has completed
+// and flushed.  Every kernel calls pdl_launch_dependents() first thing so its successor can be scheduled as soon
+// as all of its own CTAs have started.  Both instructions are no-ops for a normally launched kernel.
+bool& pdl_enabled();  // thread-local switch read by the launchers (api.cu)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ 
                                                       long long strideRk, float* __restrict__ Out,
                                                       long long strideOg, long long strideOm, int N, int mdiv,
                                                       long long strideOmLo, long long split_off) {
+  pdl_launch_dependents();
+  pdl_wait();  // R is the previous kernel's output
   constexpr int NT = TM * 4;
   constexpr int A4 = TM * KC / 4 / NT;  // float4 per thread for the A tile (= 2)
   constexpr int B4 = KC * TN / 4 / NT;  // for the B tile (2 or 4)
@@ -165,13 +167,13 @@ int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long
   if (M <= 32 || ctas64 < 2 * 148) {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 32));
     B2_CUDA(cudaFuncSetAttribute(lmul_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM32));
-    lmul_kernel<32><<<grid, 128, SM32, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
-                                          strideOmLo, split_off);
+    B2_CUDA(launch_kernel(lmul_kernel<32>, grid, dim3(128), SM32, st, L, ldl, M, K, R, strideRg, strideRk, Out, strideOg,
+                          strideOm, N, mdiv, strideOmLo, split_off));
   } else {
     dim3 grid(G, ceil_div(N, TN), ceil_div(M, 64));
     B2_CUDA(cudaFuncSetAttribute(lmul_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64));
-    lmul_kernel<64><<<grid, 256, SM64, st>>>(L, ldl, M, K, R, strideRg, strideRk, Out, strideOg, strideOm, N, mdiv,
-                                          strideOmLo, split_off);
+    B2_CUDA(launch_kernel(lmul_kernel<64>, grid, dim3(256), SM64, st, L, ldl, M, K, R, strideRg, strideRk, Out, strideOg,
+                          strideOm, N, mdiv, strideOmLo, split_off));
   }
   B2_LAUNCHED("lmul_kernel");
   return 0;
@@ -192,6 +194,8 @@ constexpr int MODES_BCH = 32;  // batch entries staged per pass
 __global__ void __launch_bounds__(256) modes_kernel(const float* __restrict__ S, const float* __restrict__ Wpk,
                                                     float* __restrict__ O, int B, int NM, int Cp) {
   extern __shared__ __align__(16) float Ss[];  // [MODES_BCH][2][Cp] inputs, then [nsl][nb][2][Cp] partials
+  pdl_launch_dependents();
+  pdl_wait();  // S is the previous kernel's output
   const int mode = blockIdx.x;
   const int OQ = Cp >> 2;      // column quads
   const int nq = min(OQ, 32);  // quads handled per sweep by threadIdx.x % nq
@@ -266,7 +270,7 @@ int launch_modes(const float* S, const float* Wpk, float* O, int B, int NM, int 
     return B200FNO_EINVAL;
   }
   B2_CUDA(cudaFuncSetAttribute(modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  modes_kernel<<<NM, 256, smem, st>>>(S, Wpk, O, B, NM, Cp);
+  B2_CUDA(launch_kernel(modes_kernel, dim3(NM), dim3(256), smem, st, S, Wpk, O, B, NM, Cp));
   B2_LAUNCHED("modes_kernel");
   return 0;
 }

@@ -36,6 +36,7 @@ struct FwdWArgs {
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
     tc_fwdw_kernel(FwdWArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sX = smem;  // FW_NS stages of [x chunk | table chunk]
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
   const uint32_t tmem = tmem_base_s;
   const uint32_t T_ACC = tmem, T_A = tmem + 64;  // acc: 2 x 32 cols; A: 2 x (64 hi | 64 lo)
 
@@ -207,7 +209,7 @@ int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, l
   a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2;
   const int smem = FW_NS * FW_STAGE + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_fwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_fwdw_kernel<<<std::min(148, a.npairs), FW_THREADS, smem, st>>>(a, tmX, tmF);
+  B2_CUDA(launch_kernel(tc_fwdw_kernel, dim3(std::min(148, a.npairs)), dim3(FW_THREADS), (size_t)smem, st, a, tmX, tmF));
   B2_LAUNCHED("tc_fwdw_kernel");
   return 0;
 }

@@ -58,6 +58,7 @@ template <int MODE, int NKL>  // NKL: K steps of the lift GEMM (0 in layer mode)
 __global__ void __launch_bounds__(TCL_THREADS, 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (no integer round trip): every derived pointer keeps its address
   // space, so plain C++ accesses below compile to LDS/STS instead of generic LD.E/ST.E
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t T_ACC = tmem, T_A = tmem + 128, T_GHI = tmem + 384, T_GLO = tmem + 448;
+  pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -423,7 +425,8 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
   a.nsx = tc_layer_nsx(a.PT);
   B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
-  tc_layer_kernel<MODE_LAYER, 0><<<a.NTW * a.G, TCL_THREADS, TCL_SMEM, st>>>(a, tmX, tmOut, tmW, tmD);
+  B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LAYER, 0>, dim3(a.NTW * a.G), dim3(TCL_THREADS), TCL_SMEM, st, a, tmX, tmOut,
+                        tmW, tmD));
   B2_LAUNCHED("tc_layer_kernel");
   return 0;
 }
@@ -467,7 +470,8 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
   case N:                                                                                                        \
     B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LIFT, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                  TCL_SMEM));                                                                     \
-    tc_layer_kernel<MODE_LIFT, N><<<grid, TCL_THREADS, TCL_SMEM, st>>>(a, tmIn, tmOut, tmW0, tmW0);              \
+    B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LIFT, N>, dim3(grid), dim3(TCL_THREADS), TCL_SMEM, st, a, tmIn, tmOut,  \
+                          tmW0, tmW0));                                                                          \
     break;
   switch (a.nkl) {
     B2_LIFT_CASE(1)

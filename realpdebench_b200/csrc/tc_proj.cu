@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     tc_proj_kernel(TcProjArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmState) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sX = smem;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t T_X = tmem, T_ACC = tmem + 128, T_H = tmem + 256;
+  pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
 
   // epilogue 1 on 16 hidden columns of this thread's TMEM lane: GELU(acc + b1) -> (hi | lo) A operand of GEMM-2
   auto epi1_chunk = [&](uint32_t lane_addr, int col0) {
@@ -401,10 +403,12 @@ int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap
   }
   if (a.out_tma) {
     B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
-    tc_proj_kernel<true><<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2, tmOut, tmState);
+    B2_CUDA(launch_kernel(tc_proj_kernel<true>, dim3(a.NTW * a.G), dim3(TCP_THREADS), (size_t)TCP_SMEM, st, a, tmX, tmW1,
+                          tmW2, tmOut, tmState));
   } else {
     B2_CUDA(cudaFuncSetAttribute(tc_proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
-    tc_proj_kernel<false><<<a.NTW * a.G, TCP_THREADS, TCP_SMEM, st>>>(a, tmX, tmW1, tmW2, tmOut, tmState);
+    B2_CUDA(launch_kernel(tc_proj_kernel<false>, dim3(a.NTW * a.G), dim3(TCP_THREADS), (size_t)TCP_SMEM, st, a, tmX, tmW1,
+                          tmW2, tmOut, tmState));
   }
   B2_LAUNCHED("tc_proj_kernel");
   return 0;

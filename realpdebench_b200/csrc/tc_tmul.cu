@@ -37,6 +37,7 @@ __device__ __forceinline__ int round_up_dev(int x, int m) { return (x + m - 1) /
 
 __global__ void __launch_bounds__(TM_THREADS, 1)
     tc_tmul_kernel(TmulArgs a, const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmL) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   __shared__ uint64_t x_full[4], x_empty[4], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t T_ACC = tmem, T_A = tmem + 256;  // acc: 2 x (<=128) cols; A: 2 x (64 hi | 64 lo)
+  pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
 
   auto decode = [&](int ip, int& g, int& nt, int& mt) {
     const int wi = blockIdx.x + ip * gridDim.x;  // m tile fastest: the data tile is re-read from L2
@@ -259,7 +261,7 @@ int launch_tmul_tc(const TmulPlan& tp, const CUtensorMap& tmR, float* out, int G
   const int items = G * a.NT * a.n_mt;
   const int smem = tp.NS * tp.stage_bytes + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_tmul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_tmul_kernel<<<std::min(148, items), TM_THREADS, smem, st>>>(a, tmR, tp.tmL);
+  B2_CUDA(launch_kernel(tc_tmul_kernel, dim3(std::min(148, items)), dim3(TM_THREADS), (size_t)smem, st, a, tmR, tp.tmL));
   B2_LAUNCHED("tc_tmul_kernel");
   return 0;
 }
