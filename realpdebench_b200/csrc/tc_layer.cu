@@ -25,8 +25,15 @@
 namespace b200fno {
 using namespace tc;
 
-constexpr int TCL_THREADS = 512;
+// 8 control / split warps + the epilogue warps, in groups of 8 (256 threads: TMEM lane quarter x channel half).
+// The epilogue of one tile is a latency chain (accumulator ready -> tcgen05.ld -> barrier -> affine + GELU -> staging ->
+// proxy fence -> barrier -> TMA store) that a single group runs one tile at a time; the layer kernel was bound by it
+// (ncu: producer, split and MMA warps asleep on their barriers, DRAM 53-64 %).  Layer mode therefore runs TWO
+// epilogue groups in ping-pong: group e drains accumulator buffer e (even / odd tiles) into its own staging buffer,
+// so two tiles' chains overlap.  The lift keeps one group (its split warps need the registers).
 constexpr int EPI_THREADS = 256;
+__host__ __device__ constexpr int tcl_groups(int mode) { return mode == 0 ? 2 : 1; }
+__host__ __device__ constexpr int tcl_threads(int mode) { return 256 + EPI_THREADS * tcl_groups(mode); }
 constexpr int NSX_MAX = 4;
 constexpr int XS_MAX = 32768;     // x stage: 2 sub-tiles (32 ch) x PT <= 128 rows x 128 B = PT*256 bytes
 constexpr int TCL_BUDGET = 225 * 1024;  // dynamic shared memory the ring / staging layout may use
@@ -55,9 +62,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 
 
 template <int MODE, int NKL>  // NKL: K steps of the lift GEMM (0 in layer mode)
-__global__ void __launch_bounds__(TCL_THREADS, 1)
+__global__ void __launch_bounds__(tcl_threads(MODE), 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
+  constexpr int TCL_THREADS = tcl_threads(MODE), NGRP = tcl_groups(MODE);
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (no integer round trip): every derived pointer keeps its address
@@ -331,12 +339,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3, half = (warp - 8) >> 2, p = q * 32 + lane, etid = tid - 256;
+    const int ew = warp - 8, grp = ew >> 3, w8 = ew & 7;  // epilogue group (0 when there is only one), warp in group
+    const int q = w8 & 3, half = w8 >> 2, p = q * 32 + lane, etid = tid - 256 - grp * EPI_THREADS;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float sc[32], sh[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) sc[i] = s_scale[half * 32 + i], sh[i] = s_shift[half * 32 + i];
-    for (int it = 0; it < n_my; ++it) {
+    for (int it = grp; it < n_my; it += NGRP) {
+      // two groups: group e owns accumulator buffer e and staging buffer e; one group: both alternate per tile
       const int row = g + it * a.G, t = it & 1, pt = (it >> 1) & 1, buf = it & 1;
       mbar_wait(&acc_full[t], pt);
       tc_fence_after();
@@ -345,21 +352,27 @@ __global__ void __launch_bounds__(TCL_THREADS, 1)
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[t]);
-      if (etid == 0) tma_store_wait_read<1>();  // the store that last used staging[buf] has read it
-      named_bar_sync(1, EPI_THREADS);
+      if (etid == 0) {  // the store that last used staging[buf] (issued by this very thread) has read it
+        if (NGRP == 2) tma_store_wait_read<0>();
+        else tma_store_wait_read<1>();
+      }
+      named_bar_sync(1 + grp, EPI_THREADS);
       const uint32_t stage = smem_u32(sOut) + buf * OS_BYTES + half * SUB;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
+        // per-channel affine from shared memory (broadcast LDS.128): keeps the epilogue under the 85-register cap
+        const float4 sc = *reinterpret_cast<const float4*>(&s_scale[half * 32 + 4 * c]);
+        const float4 sh = *reinterpret_cast<const float4*>(&s_shift[half * 32 + 4 * c]);
         float y0, y1, y2, y3;
-        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])),
-                         f2_pack(sc[4 * c], sc[4 * c + 1]), f2_pack(sh[4 * c], sh[4 * c + 1])), y0, y1);
-        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])),
-                         f2_pack(sc[4 * c + 2], sc[4 * c + 3]), f2_pack(sh[4 * c + 2], sh[4 * c + 3])), y2, y3);
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])), f2_pack(sc.x, sc.y),
+                         f2_pack(sh.x, sh.y)), y0, y1);
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3])), f2_pack(sc.z, sc.w),
+                         f2_pack(sh.z, sh.w)), y2, y3);
         if (a.gelu) gelu_erf_fast2(y0, y1), gelu_erf_fast2(y2, y3);
         if (p < PT) sts128(stage + sw128_off(p, c), y0, y1, y2, y3);  // rows >= PT lie outside the tile-sized buffer
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, EPI_THREADS);
+      named_bar_sync(1 + grp, EPI_THREADS);
       if (etid == 0) {
         const uint8_t* st = sOut + buf * OS_BYTES;
         tma_store_3d(&tmOut, st, 0, PT * j, row);
@@ -425,8 +438,8 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
   a.nsx = tc_layer_nsx(a.PT);
   B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
-  B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LAYER, 0>, dim3(a.NTW * a.G), dim3(TCL_THREADS), TCL_SMEM, st, a, tmX, tmOut,
-                        tmW, tmD));
+  B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LAYER, 0>, dim3(a.NTW * a.G), dim3(tcl_threads(MODE_LAYER)), TCL_SMEM, st, a,
+                        tmX, tmOut, tmW, tmD));
   B2_LAUNCHED("tc_layer_kernel");
   return 0;
 }
@@ -470,8 +483,8 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
   case N:                                                                                                        \
     B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LIFT, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                  TCL_SMEM));                                                                     \
-    B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LIFT, N>, dim3(grid), dim3(TCL_THREADS), TCL_SMEM, st, a, tmIn, tmOut,  \
-                          tmW0, tmW0));                                                                          \
+    B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LIFT, N>, dim3(grid), dim3(tcl_threads(MODE_LIFT)), TCL_SMEM, st, a,  \
+                          tmIn, tmOut, tmW0, tmW0));                                                             \
     break;
   switch (a.nkl) {
     B2_LIFT_CASE(1)
