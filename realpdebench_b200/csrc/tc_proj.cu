@@ -110,11 +110,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   const uint32_t T_X = tmem, T_ACC = tmem + 128, T_H = tmem + 256;
   pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
 
-  // epilogue 1 on 16 hidden columns of this thread's TMEM lane: GELU(acc + b1) -> (hi | lo) A operand of GEMM-2
-  auto epi1_chunk = [&](uint32_t lane_addr, int col0) {
-    uint32_t v[16];
-    tmem_ld16(T_ACC + lane_addr + col0, v);
-    tmem_ld_wait();
+  // epilogue 1 on 16 hidden columns of this thread's TMEM lane: GELU(acc + b1) -> (hi | lo) A operand of GEMM-2.
+  // The tcgen05.ld of all of a warp's chunks are issued up front (one wait), so only the first pays the load latency.
+  auto epi1_load = [&](uint32_t lane_addr, int col0, uint32_t (&v)[16]) { tmem_ld16(T_ACC + lane_addr + col0, v); };
+  auto epi1_store = [&](uint32_t lane_addr, int col0, uint32_t (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
       float y0 = __uint_as_float(v[i]) + s_b1[col0 + i], y1 = __uint_as_float(v[i + 1]) + s_b1[col0 + i + 1];
@@ -125,6 +124,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
 #pragma unroll
     for (int i = 0; i < 16; i += 2) tf32_lo2(v[i], v[i + 1]);
     tmem_st16(T_H + 128 + lane_addr + col0, v);
+  };
+  auto epi1_publish = [&](int chunk) {  // call after tmem_st_wait(): the chunk's hidden quarter may feed GEMM-2
+    mbar_arrive(&h_full[chunk >> 1]);
   };
 
   auto padded_row = [&](int row) {  // valid row (b, t, h) -> row of the padded activation grid
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4, p = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    for (int it = 0; it < n_my; ++it) {
+    // x tile `it` -> TMEM (x_hi | x_lo) as the A operand of GEMM-1
+    auto stage_x = [&](int it) {
       const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
       mbar_wait(&x_full[sx], px);
       mbar_wait(&xa_empty, (it & 1) ^ 1);
@@ -235,16 +238,28 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&xa_full);
-      // this warp's share of epilogue 1 for the same tile: hidden columns [96, 128)
+    };
+    if (n_my > 0) stage_x(0);
+    for (int it = 0; it < n_my; ++it) {
       mbar_wait(&acc1_full, it & 1);
+      // GEMM-1 of this tile has finished with the x operand (xa_empty is committed together with acc1_full): stage
+      // the NEXT tile now, so that GEMM-1(it+1) can start the moment epilogue 2 has drained the accumulator, instead
+      // of after this warp's epilogue-1 chunks
+      if (it + 1 < n_my) stage_x(it + 1);
       tc_fence_after();
-      // round-robin over the three warps of a lane quarter (see the epilogue warps): chunks 2 and 5
-#pragma unroll
-      for (int chunk = 2; chunk < 8; chunk += 3) {
-        epi1_chunk(lane_addr, chunk * 16);
+      // this warp's share of epilogue 1: round-robin over the three warps of a lane quarter, chunks 2 and 5
+      {
+        uint32_t v0[16], v1[16];
+        epi1_load(lane_addr, 2 * 16, v0), epi1_load(lane_addr, 5 * 16, v1);
+        tmem_ld_wait();
+        epi1_store(lane_addr, 2 * 16, v0);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&h_full[chunk >> 1]);
+        epi1_publish(2);
+        epi1_store(lane_addr, 5 * 16, v1);
+        tmem_st_wait();
+        tc_fence_before();
+        epi1_publish(5);
       }
     }
   } else if (warp >= 8) {
@@ -268,12 +283,22 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       tc_fence_after();
       // sixteen-column chunks in increasing order across the three warps of a lane quarter (hh = 0: 0,3,6;
       // hh = 1: 1,4,7; split warp: 2,5): low hidden quarters complete first and GEMM-2 starts on them early
-#pragma unroll
-      for (int chunk = hh; chunk < 8; chunk += 3) {
-        epi1_chunk(lane_addr, chunk * 16);
+      {
+        uint32_t v0[16], v1[16], v2[16];
+        epi1_load(lane_addr, hh * 16, v0), epi1_load(lane_addr, (hh + 3) * 16, v1), epi1_load(lane_addr, (hh + 6) * 16, v2);
+        tmem_ld_wait();
+        epi1_store(lane_addr, hh * 16, v0);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&h_full[chunk >> 1]);
+        epi1_publish(hh);
+        epi1_store(lane_addr, (hh + 3) * 16, v1);
+        tmem_st_wait();
+        tc_fence_before();
+        epi1_publish(hh + 3);
+        epi1_store(lane_addr, (hh + 6) * 16, v2);
+        tmem_st_wait();
+        tc_fence_before();
+        epi1_publish(hh + 6);
       }
       // ---- epilogue 2: + b2, rollout affine, scatter to the prediction slice and the next model input
       mbar_wait(&acc2_full, ph);
