@@ -191,7 +191,7 @@ constexpr int MODES_BCH = 32;  // batch entries staged per pass
 // at B = 8) most groups would otherwise idle while a few threads walk all Cp input channels with two
 // dependent-latency weight loads per step; slicing i keeps every thread busy and 4x more loads in
 // flight.  Partial sums of the slices are reduced through shared memory.
-__global__ void __launch_bounds__(256) modes_kernel(const float* __restrict__ S, const float* __restrict__ Wpk,
+__global__ void __launch_bounds__(256, 4) modes_kernel(const float* __restrict__ S, const float* __restrict__ Wpk,
                                                     float* __restrict__ O, int B, int NM, int Cp) {
   extern __shared__ __align__(16) float Ss[];  // [MODES_BCH][2][Cp] inputs, then [nsl][nb][2][Cp] partials
   pdl_launch_dependents();
