@@ -33,7 +33,12 @@ using namespace tc;
 // so two tiles' chains overlap.  The lift keeps one group (its split warps need the registers).
 constexpr int EPI_THREADS = 256;
 __host__ __device__ constexpr int tcl_groups(int mode) { return mode == 0 ? 2 : 1; }
-__host__ __device__ constexpr int tcl_threads(int mode) { return 256 + EPI_THREADS * tcl_groups(mode); }
+// The lift is bound by its split warps (the feature gather): it runs a second group of four (warps 16-19) in
+// ping-pong with warps 4-7, one group per A-operand buffer (even / odd tiles).
+__host__ __device__ constexpr int tcl_split_groups(int mode) { return mode == 0 ? 1 : 2; }
+__host__ __device__ constexpr int tcl_threads(int mode) {
+  return 256 + EPI_THREADS * tcl_groups(mode) + 128 * (tcl_split_groups(mode) - 1);
+}
 constexpr int NSX_MAX = 4;
 constexpr int XS_MAX = 32768;     // x stage: 2 sub-tiles (32 ch) x PT <= 128 rows x 128 B = PT*256 bytes
 constexpr int TCL_BUDGET = 225 * 1024;  // dynamic shared memory the ring / staging layout may use
@@ -65,7 +70,7 @@ template <int MODE, int NKL>  // NKL: K steps of the lift GEMM (0 in layer mode)
 __global__ void __launch_bounds__(tcl_threads(MODE), 1)
     tc_layer_kernel(TcLayerArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD) {
-  constexpr int TCL_THREADS = tcl_threads(MODE), NGRP = tcl_groups(MODE);
+  constexpr int TCL_THREADS = tcl_threads(MODE), NGRP = tcl_groups(MODE), NSG = tcl_split_groups(MODE);
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (no integer round trip): every derived pointer keeps its address
@@ -225,9 +230,10 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
       }
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 8 + 8 * NGRP) {
     // ------------------------------------------------------------------ split warps (A operand producers)
-    const int q = warp - 4, p = q * 32 + lane;
+    const int q = warp & 3, p = q * 32 + lane;  // TMEM lane quarter = warp % 4
+    const int sgrp = warp >= 8 ? 1 : 0;          // split group (lift: warps 16-19 take the odd tiles)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     if (MODE == MODE_LAYER) {  // inverse-W table rows of this W tile -> TMEM, once
       const int w = PT * j + p;
@@ -280,8 +286,8 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
         for (int f = 0; f < NIN; ++f)
           if (f < a.Fin) r[f] = valid ? __float_as_uint(__ldg(xp + s_inoff[f])) : 0u;
       };
-      gather(0);
-      for (int it = 0; it < n_my; ++it) {
+      if (sgrp < n_my) gather(sgrp);
+      for (int it = sgrp; it < n_my; it += NSG) {
         const int t = it & 1, pt = (it >> 1) & 1;
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
           tmem_st8(Ahi + k0, hi);
           tmem_st8(Alo + k0, lo);
         }
-        if (it + 1 < n_my) gather(it + 1);
+        if (it + NSG < n_my) gather(it + NSG);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_full[t]);
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
       tc_fence_before();
       mbar_arrive(&a_full[t]);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 8 + 8 * NGRP) {
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 8, grp = ew >> 3, w8 = ew & 7;  // epilogue group (0 when there is only one), warp in group
     const int q = w8 & 3, half = w8 >> 2, p = q * 32 + lane, etid = tid - 256 - grp * EPI_THREADS;
