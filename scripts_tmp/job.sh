@@ -1,5 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_torch_path_timing.py 2>&1 | tail -2
-timeout 300 python bench.py --no-cpu-baseline 2>gpurun_out/bench_pp.err | tail -1 > gpurun_out/bench_pp.json; python -c "
-import json; d=json.loads(open('gpurun_out/bench_pp.json').read()); print(d['value'], d['ms_per_step'], d['stages_ms_per_rollout'], d['roofline']['frac'], d['clocks'])"
-timeout 300 python bench.py --workload fno3d_cylinder_64x128_rollout10 --steps 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('3D', d['value'], d['ms_per_step'], d['stages_ms_per_rollout']['lift'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+cat gpurun_out/torch_gpu_path.json; echo
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 300 python bench.py > gpurun_out/bench_final.json 2>gpurun_out/bench_final.err; tail -1 gpurun_out/bench_final.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('2D', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['whole_step']['frac_of_hbm_peak'], d['clocks'], d['gpu_launches'])"
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
