@@ -389,9 +389,9 @@ int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
     set_error("bad impl selector");
     return B200FNO_EINVAL;
   }
-  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p;
+  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp;
   if (impl == B200FNO_IMPL_TC && !can_tc) {
-    set_error("tensor-core layer kernel needs width 64 and modes3 in {4,8,12,16}; got width %d, modes3 %d",
+    set_error("tensor-core layer kernel needs width 64 and modes3 a multiple of 4 up to 32; got width %d, modes3 %d",
               p->d.width, p->d.modes3);
     return B200FNO_EINVAL;
   }
@@ -404,7 +404,7 @@ int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
 }
 int b200fno_plan_get_impl(const b200fno_plan_t* p) {
   if (!p) return B200FNO_EINVAL;
-  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p;
+  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp;
   return (p->impl_request != B200FNO_IMPL_SIMT && can_tc) ? B200FNO_IMPL_TC : B200FNO_IMPL_SIMT;
 }
 
@@ -478,15 +478,28 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   p->fc1W = q, q += align_up((size_t)128 * g.Cp, 64);
   p->fc2W = q;
   p->weights_ready = false;
-  p->use_tc = p->impl_request != B200FNO_IMPL_SIMT && tc_layer_supported(g) && g.K2 == g.K2p;
-  if (p->use_tc) {
-    const long long rows = (long long)B * g.Tp * g.Hp;
+  p->use_tc = p->impl_request != B200FNO_IMPL_SIMT && tc_layer_supported(g) && g.K2 == g.K2p && p->d.width == g.Cp;
+  // the lift and the projection do not depend on the mode count: they run on the tensor cores for every width-64
+  // model, also where the layer kernel itself has to fall back to the FFMA version (modes3 > 32)
+  const bool tc64 = p->impl_request != B200FNO_IMPL_SIMT && g.Cp == 64 && p->d.width == 64;
+  const long long rows = (long long)B * g.Tp * g.Hp;
+  p->use_tc_lift = p->use_tc_proj = false;
+  if (p->use_tc || tc64) {
     B2_TRY(tc_make_act_map(&p->tmAct[0], p->act[0], rows, g));
     B2_TRY(tc_make_act_map(&p->tmAct[1], p->act[1], rows, g));
-    B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
-    for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
     p->use_tc_lift = tc_lift_nkl(p->Fin) > 0;
     if (p->use_tc_lift) B2_TRY(tc_make_w_map(&p->tmW0, p->W0K));
+    p->use_tc_proj = tc_proj_supported(g, p->Fout);
+    if (p->use_tc_proj) {
+      B2_TRY(tc_make_proj_act_map(&p->tmActProj[0], p->act[0], rows, g, p->d.w));
+      B2_TRY(tc_make_proj_act_map(&p->tmActProj[1], p->act[1], rows, g, p->d.w));
+      B2_TRY(tc_make_fc1_map(&p->tmFc1, p->fc1HL));
+      B2_TRY(tc_make_fc2_map(&p->tmFc2, p->fc2HL, tc_proj_n2(p->Fout)));
+    }
+  }
+  if (p->use_tc) {
+    B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
+    for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
     {  // H / T axis transforms on the tensor cores
       const Tables& tb = p->tab;
       const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw, GT = B * g.Tp;
@@ -505,13 +518,6 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
     if (p->use_tc_fwdw) {
       B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], p->tab.LF_hl, rows, g));
       B2_TRY(tc_make_fwdw_maps(&p->tmFwX[1], &p->tmFwF, p->act[1], p->tab.LF_hl, rows, g));
-    }
-    p->use_tc_proj = tc_proj_supported(g, p->Fout);
-    if (p->use_tc_proj) {
-      B2_TRY(tc_make_proj_act_map(&p->tmActProj[0], p->act[0], rows, g, p->d.w));
-      B2_TRY(tc_make_proj_act_map(&p->tmActProj[1], p->act[1], rows, g, p->d.w));
-      B2_TRY(tc_make_fc1_map(&p->tmFc1, p->fc1HL));
-      B2_TRY(tc_make_fc2_map(&p->tmFc2, p->fc2HL, tc_proj_n2(p->Fout)));
     }
   }
   return 0;

@@ -43,7 +43,8 @@ constexpr int NSX_MAX = 4;
 constexpr int XS_MAX = 32768;     // x stage: 2 sub-tiles (32 ch) x PT <= 128 rows x 128 B = PT*256 bytes
 constexpr int TCL_BUDGET = 225 * 1024;  // dynamic shared memory the ring / staging layout may use
 constexpr int W_BYTES = 32768;    // conv weights hi | lo, each 2 sub-tiles x 64 rows x 128 B
-constexpr int DS_BYTES = 16384;   // D stage: 2 N-blocks x (2*K2p <= 64) k-rows x 128 B
+constexpr int DS_BYTES = 16384;   // minimum D stage (also the lift's table area); a stage is 2 N-blocks x 2*K2p k-rows x 128 B
+__host__ __device__ constexpr int tcl_ds_bytes(int K2p) { return 512 * K2p > DS_BYTES ? 512 * K2p : DS_BYTES; }
 constexpr int TCL_SMEM = TCL_BUDGET + 1024;
 
 enum { MODE_LAYER = 0, MODE_LIFT = 1 };
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = blockIdx.x % a.NTW, g = blockIdx.x / a.NTW;
   const int n_my = g < a.rows ? (a.rows - g + a.G - 1) / a.G : 0;
-  const int PT = a.PT, K2p = a.K2p;
+  const int PT = a.PT, K2p = a.K2p, DSB = tcl_ds_bytes(a.K2p);  // D stage bytes
 
   if (tid == 0) {
     for (int i = 0; i < NSX_MAX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 4);
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
       mbar_wait(&d_empty[sd], pd ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&d_full[sd], (uint32_t)(2 * 2 * K2p * 128));
-        tma_load_2d(sD + sd * DS_BYTES, &tmD, &d_full[sd], 0, row * 2 * K2p);
-        tma_load_2d(sD + sd * DS_BYTES + 2 * K2p * 128, &tmD, &d_full[sd], 32, row * 2 * K2p);
+        tma_load_2d(sD + sd * DSB, &tmD, &d_full[sd], 0, row * 2 * K2p);
+        tma_load_2d(sD + sd * DSB + 2 * K2p * 128, &tmD, &d_full[sd], 32, row * 2 * K2p);
       }
       __syncwarp();
     }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
       const uint32_t acc = T_ACC + t * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
       // descriptor "lo word" offsets are in 16-byte units: k-step ks of a K-major operand sits at
       // sub-tile (ks/4) * 8192 B + (ks%4) * 32 B; of the MN-major D operand at ks * 8 rows * 128 B
-      const uint64_t dD_hi = make_smem_desc(smem_u32(sD) + t * DS_BYTES, 2 * K2p * 128, 512, LAYOUT_SW128_BASE32B);
+      const uint64_t dD_hi = make_smem_desc(smem_u32(sD) + t * DSB, 2 * K2p * 128, 512, LAYOUT_SW128_BASE32B);
       const uint64_t dD_lo = dD_hi + (uint64_t)(K2p * 128 >> 4);
       if (elect_one_sync()) {
         if (MODE == MODE_LIFT) {
@@ -212,16 +213,16 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
           for (int ks = 0; ks < 8; ++ks)
             umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
+          for (int ks = 0; ks < 8; ++ks)
             if (ks < nk2) umma_tf32_ts(acc, T_GLO + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
+          for (int ks = 0; ks < 8; ++ks)
             if (ks < nk2) umma_tf32_ts(acc, T_GHI + ks * 8, dD_lo + (uint64_t)(ks * 64), idesc_d, 1);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_tf32_ts(acc, Ahi + ks * 8, dW_hi + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
+          for (int ks = 0; ks < 8; ++ks)
             if (ks < nk2) umma_tf32_ts(acc, T_GHI + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, 1);
           umma_commit(&d_empty[t]);
         }
@@ -395,13 +396,13 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
 
 // ---------------------------------------------------------------------------------------------
 bool tc_layer_supported(const Geom& g) {
-  return g.Cp == 64 && g.K2p % 8 == 0 && g.K2p <= 32 && ceil_div(g.Wp, 128) <= 148;
+  return g.Cp == 64 && g.K2p % 8 == 0 && g.K2p <= 64 && ceil_div(g.Wp, 128) <= 148;  // G rows: 2 x 64 TMEM columns
 }
 
 // x-ring depth that fits next to 2 staging buffers, the weights and the D ring
-int tc_layer_nsx(int PT) {
+int tc_layer_nsx(int PT, int K2p) {
   const int stage = PT * 256;
-  return std::max(2, std::min(NSX_MAX, (TCL_BUDGET - 2 * stage - W_BYTES - 2 * DS_BYTES) / stage));
+  return std::max(2, std::min(NSX_MAX, (TCL_BUDGET - 2 * stage - W_BYTES - 2 * tcl_ds_bytes(K2p)) / stage));
 }
 
 int tc_layer_tile(const Geom& g, int* PT, int* NTW) {
@@ -442,7 +443,7 @@ int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUte
   a.Gt = Gt, a.scale = scale, a.shift = shift;
   a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
-  a.nsx = tc_layer_nsx(a.PT);
+  a.nsx = tc_layer_nsx(a.PT, a.K2p);
   B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
   B2_CUDA(launch_kernel(tc_layer_kernel<MODE_LAYER, 0>, dim3(a.NTW * a.G), dim3(tcl_threads(MODE_LAYER)), TCL_SMEM, st, a,
                         tmX, tmOut, tmW, tmD));
@@ -459,7 +460,7 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
   tc_layer_tile(g, &a.PT, &a.NTW);
   a.rows = la.B * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
-  a.nsx = tc_layer_nsx(a.PT);
+  a.nsx = tc_layer_nsx(a.PT, 0);  // the lift has no D ring (that area holds its gather tables)
   a.x = la.x, a.in_off = la.in_off, a.gt = la.gt, a.gh = la.gh, a.gw = la.gw;
   a.Tv = la.T, a.H = la.H, a.W = la.W, a.Tp = g.Tp, a.Hp = g.Hp, a.c_in = la.c_in, a.Fin = la.Fin, a.ng = la.ng;
   a.nkl = tc_lift_nkl(la.Fin);

@@ -1,6 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-cat gpurun_out/torch_gpu_path.json; echo
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 300 python bench.py > gpurun_out/bench_final.json 2>gpurun_out/bench_final.err; tail -1 gpurun_out/bench_final.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('2D', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['whole_step']['frac_of_hbm_peak'], d['clocks'], d['gpu_launches'])"
-timeout 200 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_torch_path_timing.py 2>&1 | tail -4
+rm -f gpurun_out/c5_sweep2.jsonl
+for k in 12 16 24 32 48 64; do timeout 200 python bench.py --workload fno2d_modes${k}_256x256 --steps 20 --e2e-steps 2 --no-cpu-baseline 2>/dev/null | tail -1 >> gpurun_out/c5_sweep2.jsonl; done
+python - <<'PY'
+import json
+for l in open('gpurun_out/c5_sweep2.jsonl'):
+    d=json.loads(l); print(d['config']['workload'], round(d['ms_per_step'],3), d['stages_ms_per_rollout'])
+PY

@@ -224,7 +224,8 @@ def test_c4_combustion_shape_3d(R):
 @pytest.mark.parametrize("k", [12, 16, 24, 32, 48, 64])
 def test_c5_mode_sweep_2d(R, k):
     """BASELINE config C5: FNO-2D mode-count sweep at a 256^2 grid, one frame x 3 ch, width 64.
-    k <= 16 runs on the tensor-core kernels, larger mode counts on the FFMA kernels."""
+    k <= 32 runs the layer kernel on the tensor cores (K2 = 2k <= 64 inverse-W rows fit its TMEM / shared-memory budget),
+    larger mode counts on the FFMA layer kernel; lift and projection are tensor-core kernels for every k."""
     torch.manual_seed(50 + k)
     s = (1, 256, 256, 3)
     sd = O.init_state(2, (k, k), 4, 64, s, s)
@@ -234,7 +235,7 @@ def test_c5_mode_sweep_2d(R, k):
     m = m.to(dev()).eval()
     x = torch.randn(2, *s)
     y = m(x.to(dev())).cpu()
-    assert m.engine.resolved_impl() == ("tc" if k in (12, 16) else "simt")
+    assert m.engine.resolved_impl() == ("tc" if k <= 32 else "simt")
     assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
 
 
