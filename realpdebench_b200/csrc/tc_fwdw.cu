@@ -1,4 +1,4 @@
-// Forward W transform of the truncated DFT on the tensor cores (width 64, 2*m3 in {16, 32}):
+// Forward W transform of the truncated DFT on the tensor cores (width 64, 2*m3 in {16, 32, 48, 64}):
 //
 //   A[row][k][c] = sum_w LF[k][w] * x[row][w][c]          (rfftn's last axis, kept modes only; fno.py:48,53)
 //
@@ -26,12 +26,11 @@ constexpr int FW_THREADS = 384;
 constexpr int FW_NS = 4;          // ring stages
 constexpr int FW_CH = 64;         // points per chunk
 constexpr int FW_XS = 32768;      // x part of a stage: 2 channel halves x 2 rows x 64 points x 128 B
-constexpr int FW_FS = 16384;      // table part: [hi|lo][2 sub-tiles of 32 points][K2 <= 32 rows][128 B]
-constexpr int FW_STAGE = FW_XS + FW_FS;
+// table part of a stage: [hi|lo][2 sub-tiles of 32 points][K2 rows][128 B] = 512*K2 bytes (16-32 KB)
 
 struct FwdWArgs {
   float* out;  // [rows][K2][64]
-  int rows, npairs, nchunk, nsub, K2;
+  int rows, npairs, nchunk, nsub, K2, ns, stage_bytes;  // ns ring stages of stage_bytes (x chunk + table chunk)
 };
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
@@ -43,7 +42,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   __shared__ uint64_t x_full[FW_NS], x_empty[FW_NS], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K2 = a.K2, nchunk = a.nchunk;
+  const int K2 = a.K2, nchunk = a.nchunk, NS = a.ns, FW_STAGE = a.stage_bytes;
   const int n_my = (int)blockIdx.x < a.npairs ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
@@ -62,14 +61,14 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   tc_fence_after();
   pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
   const uint32_t tmem = tmem_base_s;
-  const uint32_t T_ACC = tmem, T_A = tmem + 64;  // acc: 2 x 32 cols; A: 2 x (64 hi | 64 lo)
+  const uint32_t T_ACC = tmem, T_A = tmem + 128;  // acc: 2 x 64 cols (K2 <= 64 used); A: 2 x (64 hi | 64 lo)
 
   if (warp == 0) {
     int cc = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       const int pair = a.npairs - 1 - (blockIdx.x + ip * gridDim.x);  // reverse order: see launch_fwdw_tc
       for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % FW_NS, px = (cc / FW_NS) & 1;
+        const int sx = cc % NS, px = (cc / NS) & 1;
         mbar_wait(&x_empty[sx], px ^ 1);
         if (elect_one_sync()) {
           uint8_t* st = sX + sx * FW_STAGE;
@@ -91,11 +90,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
       const int ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_empty[ab], pab ^ 1);
       for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int t = cc & 1, pt = (cc >> 1) & 1, sx = cc % FW_NS;
-        mbar_wait(&x_full[sx], (cc / FW_NS) & 1);  // table chunk of this stage has landed
+        const int t = cc & 1, pt = (cc >> 1) & 1, sx = cc % NS;
+        mbar_wait(&x_full[sx], (cc / NS) & 1);  // table chunk of this stage has landed
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
-        const uint32_t acc = T_ACC + ab * 32, Ahi = T_A + t * 128, Alo = Ahi + 64;
+        const uint32_t acc = T_ACC + ab * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
         const uint64_t dF_hi = make_smem_desc(smem_u32(sX) + sx * FW_STAGE + FW_XS, 0, 1024);
         const uint64_t dF_lo = dF_hi + 2 * sub;
         const uint64_t o0 = 0;
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
     int cc = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % FW_NS, px = (cc / FW_NS) & 1, t = cc & 1, pt = (cc >> 1) & 1;
+        const int sx = cc % NS, px = (cc / NS) & 1, t = cc & 1, pt = (cc >> 1) & 1;
         mbar_wait(&x_full[sx], px);
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
@@ -159,17 +158,21 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
       const int pair = a.npairs - 1 - (blockIdx.x + ip * gridDim.x), ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_full[ab], pab);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(T_ACC + ab * 32 + lane_addr, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
       const int row = 2 * pair + r;
-      if (row < a.rows) {
-        float* o = a.out + (size_t)row * K2 * 64 + c;
+      float* o = a.out + (size_t)row * K2 * 64 + c;
+      for (int c0 = 0; c0 < K2; c0 += 32) {  // 32 accumulator columns (= output rows k) per pass
+        uint32_t v[32];
+        tmem_ld32(T_ACC + ab * 64 + lane_addr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= K2) {  // last pass: the accumulator buffer is free again
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+        }
+        if (row < a.rows) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (k < K2) o[(size_t)k * 64] = __uint_as_float(v[k]);
+          for (int k = 0; k < 32; ++k)
+            if (c0 + k < K2) o[(size_t)(c0 + k) * 64] = __uint_as_float(v[k]);
+        }
       }
     }
   }
@@ -179,7 +182,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-bool tc_fwdw_supported(const Geom& g) { return g.Cp == 64 && g.K2 == g.K2p && (g.K2 == 16 || g.K2 == 32); }
+bool tc_fwdw_supported(const Geom& g) {  // MMA N = K2 must be a multiple of 16; two 64-column accumulators
+  return g.Cp == 64 && g.K2 == g.K2p && g.K2 % 16 == 0 && g.K2 <= 64;
+}
 int tc_fwdw_nsub(const Geom& g) { return 2 * ceil_div(g.Wp, FW_CH); }
 // table planes [2 (hi|lo)][K2 rows][nsub*32 points], zero padded
 size_t tc_fwdw_table_floats(const Geom& g) { return (size_t)2 * g.K2 * tc_fwdw_nsub(g) * 32; }
@@ -207,7 +212,9 @@ int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, l
   FwdWArgs a{};
   a.out = out, a.rows = (int)rows, a.npairs = (int)((rows + 1) / 2);
   a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2;
-  const int smem = FW_NS * FW_STAGE + 1024;
+  a.stage_bytes = FW_XS + round_up(512 * g.K2, 1024);
+  a.ns = std::min(FW_NS, (226 * 1024) / a.stage_bytes);
+  const int smem = a.ns * a.stage_bytes + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_fwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   B2_CUDA(launch_kernel(tc_fwdw_kernel, dim3(std::min(148, a.npairs)), dim3(FW_THREADS), (size_t)smem, st, a, tmX, tmF));
   B2_LAUNCHED("tc_fwdw_kernel");
