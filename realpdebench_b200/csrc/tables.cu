@@ -99,9 +99,10 @@ int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<fl
 int build_tables(const Geom& g, int m1, int m2, Tables* t) {
   std::vector<float> host[6];
   B2_TRY(compute_tables_host(g, m1, m2, t, host));
-  {  // forward-W table as 3xTF32 planes for the tensor-core kernel: [hi|lo][K2][wpad], zero padded
-    const int wpad = 2 * ceil_div(g.Wp, 64) * 32;
-    std::vector<float> hl((size_t)2 * g.K2 * wpad, 0.f);
+  {  // forward-W table as 3xTF32 planes for the tensor-core kernel: [hi|lo][K2m][wpad], zero padded (K2m = K2 rounded
+     // up to 16, the MMA N step)
+    const int wpad = 2 * ceil_div(g.Wp, 64) * 32, K2m = round_up(g.K2, 16);
+    std::vector<float> hl((size_t)2 * K2m * wpad, 0.f);
     for (int k = 0; k < g.K2; ++k)
       for (int w = 0; w < g.Wp; ++w) {
         const float x = host[0][(size_t)k * t->ldLF + w];
@@ -111,7 +112,7 @@ int build_tables(const Geom& g, int m1, int m2, Tables* t) {
         float hi;
         memcpy(&hi, &u, 4);
         hl[(size_t)k * wpad + w] = hi;
-        hl[((size_t)g.K2 + k) * wpad + w] = x - hi;
+        hl[((size_t)K2m + k) * wpad + w] = x - hi;
       }
     B2_CUDA(cudaMalloc((void**)&t->LF_hl, hl.size() * sizeof(float)));
     B2_CUDA(cudaMemcpy(t->LF_hl, hl.data(), hl.size() * sizeof(float), cudaMemcpyHostToDevice));

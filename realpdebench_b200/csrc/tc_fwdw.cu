@@ -30,7 +30,7 @@ constexpr int FW_XS = 32768;      // x part of a stage: 2 channel halves x 2 row
 
 struct FwdWArgs {
   float* out;  // [rows][K2][64]
-  int rows, npairs, nchunk, nsub, K2, ns, stage_bytes;  // ns ring stages of stage_bytes (x chunk + table chunk)
+  int rows, npairs, nchunk, nsub, K2, K2m, ns, stage_bytes;  // K2 output rows; K2m = K2 rounded up to the MMA N step (16)  // ns ring stages of stage_bytes (x chunk + table chunk)
 };
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   __shared__ uint64_t x_full[FW_NS], x_empty[FW_NS], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K2 = a.K2, nchunk = a.nchunk, NS = a.ns, FW_STAGE = a.stage_bytes;
+  const int K2 = a.K2m, K2out = a.K2, nchunk = a.nchunk, NS = a.ns, FW_STAGE = a.stage_bytes;  // K2: MMA N / table rows
   const int n_my = (int)blockIdx.x < a.npairs ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
@@ -64,11 +64,10 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   const uint32_t T_ACC = tmem, T_A = tmem + 128;  // acc: 2 x 64 cols (K2 <= 64 used); A: 2 x (64 hi | 64 lo)
 
   if (warp == 0) {
-    int cc = 0;
+    int sx = 0, px = 0;  // ring stage and its phase, advanced incrementally (NS is a run-time value: no div / mod)
     for (int ip = 0; ip < n_my; ++ip) {
       const int pair = a.npairs - 1 - (blockIdx.x + ip * gridDim.x);  // reverse order: see launch_fwdw_tc
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % NS, px = (cc / NS) & 1;
+      for (int ch = 0; ch < nchunk; ++ch, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
         mbar_wait(&x_empty[sx], px ^ 1);
         if (elect_one_sync()) {
           uint8_t* st = sX + sx * FW_STAGE;
@@ -85,13 +84,13 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, K2, 0, 0);
     const uint64_t sub = (uint64_t)(K2 * 128 >> 4);  // one 32-point sub-tile of the table, 16-byte units
-    int cc = 0;
+    int cc = 0, sx = 0, px = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       const int ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_empty[ab], pab ^ 1);
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int t = cc & 1, pt = (cc >> 1) & 1, sx = cc % NS;
-        mbar_wait(&x_full[sx], (cc / NS) & 1);  // table chunk of this stage has landed
+      for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
+        const int t = cc & 1, pt = (cc >> 1) & 1;
+        mbar_wait(&x_full[sx], px);  // table chunk of this stage has landed
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
         const uint32_t acc = T_ACC + ab * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
@@ -121,10 +120,10 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
     const int q = warp - 4;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t col_base = (uint32_t)((q & 1) * 16384 + (q >> 1) * 8192 + lane * 4);
-    int cc = 0;
+    int cc = 0, sx = 0, px = 0;
     for (int ip = 0; ip < n_my; ++ip) {
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % NS, px = (cc / NS) & 1, t = cc & 1, pt = (cc >> 1) & 1;
+      for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
+        const int t = cc & 1, pt = (cc >> 1) & 1;
         mbar_wait(&x_full[sx], px);
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
       mbar_wait(&acc_full[ab], pab);
       tc_fence_after();
       const int row = 2 * pair + r;
-      float* o = a.out + (size_t)row * K2 * 64 + c;
+      float* o = a.out + (size_t)row * K2out * 64 + c;
       for (int c0 = 0; c0 < K2; c0 += 32) {  // 32 accumulator columns (= output rows k) per pass
         uint32_t v[32];
         tmem_ld32(T_ACC + ab * 64 + lane_addr + c0, v);
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
         if (row < a.rows) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (c0 + k < K2) o[(size_t)(c0 + k) * 64] = __uint_as_float(v[k]);
+            if (c0 + k < K2out) o[(size_t)(c0 + k) * 64] = __uint_as_float(v[k]);
         }
       }
     }
@@ -182,12 +181,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-bool tc_fwdw_supported(const Geom& g) {  // MMA N = K2 must be a multiple of 16; two 64-column accumulators
-  return g.Cp == 64 && g.K2 == g.K2p && g.K2 % 16 == 0 && g.K2 <= 64;
-}
+int tc_fwdw_k2m(const Geom& g) { return round_up(g.K2, 16); }  // MMA N: table rows padded with zeros
+bool tc_fwdw_supported(const Geom& g) { return g.Cp == 64 && g.K2 == g.K2p && g.K2 <= 64; }  // two 64-column accumulators
 int tc_fwdw_nsub(const Geom& g) { return 2 * ceil_div(g.Wp, FW_CH); }
 // table planes [2 (hi|lo)][K2 rows][nsub*32 points], zero padded
-size_t tc_fwdw_table_floats(const Geom& g) { return (size_t)2 * g.K2 * tc_fwdw_nsub(g) * 32; }
+size_t tc_fwdw_table_floats(const Geom& g) { return (size_t)2 * tc_fwdw_k2m(g) * tc_fwdw_nsub(g) * 32; }
 
 int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, const float* table, long long rows,
                       const Geom& g) {
@@ -198,9 +196,9 @@ int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, cons
     B2_TRY(encode_tensor_map(tmX, act, 3, dims, strides, box, 0));
   }
   const int wpad = tc_fwdw_nsub(g) * 32;
-  uint64_t dims[2] = {(uint64_t)wpad, (uint64_t)2 * g.K2};
+  uint64_t dims[2] = {(uint64_t)wpad, (uint64_t)2 * tc_fwdw_k2m(g)};
   uint64_t strides[1] = {(uint64_t)wpad * 4};
-  uint32_t box[2] = {32, (uint32_t)g.K2};
+  uint32_t box[2] = {32, (uint32_t)tc_fwdw_k2m(g)};
   return encode_tensor_map(tmF, table, 2, dims, strides, box, 1);
 }
 
@@ -211,8 +209,8 @@ int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, l
                    cudaStream_t st) {
   FwdWArgs a{};
   a.out = out, a.rows = (int)rows, a.npairs = (int)((rows + 1) / 2);
-  a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2;
-  a.stage_bytes = FW_XS + round_up(512 * g.K2, 1024);
+  a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2, a.K2m = tc_fwdw_k2m(g);
+  a.stage_bytes = FW_XS + round_up(512 * a.K2m, 1024);
   a.ns = std::min(FW_NS, (226 * 1024) / a.stage_bytes);
   const int smem = a.ns * a.stage_bytes + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_fwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
