@@ -72,12 +72,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
   };
 
   if (warp == 0) {
-    int cc = 0;
+    int sx = 0, px = 0;  // ring stage / phase advanced incrementally (NS is a run-time value)
     for (int ip = 0; ip < n_my; ++ip) {
       int g, nt, mt;
       decode(ip, g, nt, mt);
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % NS, px = (cc / NS) & 1;
+      for (int ch = 0; ch < nchunk; ++ch, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
         mbar_wait(&x_empty[sx], px ^ 1);
         if (elect_one_sync()) {
           uint8_t* st = smem + sx * SB;
@@ -96,13 +95,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, MT, 0, 0);
     const uint64_t sub = (uint64_t)(MT * 128 >> 4);
-    int cc = 0;
+    int cc = 0, sx = 0, px = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       const int ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_empty[ab], pab ^ 1);
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int t = cc & 1, pt = (cc >> 1) & 1, sx = cc % NS;
-        mbar_wait(&x_full[sx], (cc / NS) & 1);
+      for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
+        const int t = cc & 1, pt = (cc >> 1) & 1;
+        mbar_wait(&x_full[sx], px);
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
         const uint32_t acc = T_ACC + ab * 128, Ahi = T_A + t * 128, Alo = Ahi + 64;
@@ -131,10 +130,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
     const int q = warp - 4;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t col_base = (uint32_t)((q & 1) * 16384 + (q >> 1) * 8192 + lane * 4);
-    int cc = 0;
+    int cc = 0, sx = 0, px = 0;
     for (int ip = 0; ip < n_my; ++ip) {
-      for (int ch = 0; ch < nchunk; ++ch, ++cc) {
-        const int sx = cc % NS, px = (cc / NS) & 1, t = cc & 1, pt = (cc >> 1) & 1;
+      for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
+        const int t = cc & 1, pt = (cc >> 1) & 1;
         mbar_wait(&x_full[sx], px);
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
