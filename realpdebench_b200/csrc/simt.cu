@@ -79,9 +79,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int LM_STAGES = 4;  // K chunks in flight: these GEMMs are skinny, the K loop is latency-bound
+// K chunks in flight (template parameter NSTG): 4 for long contractions (latency-bound K loop), 2 when the whole
+// contraction is at most two chunks (inverse transforms, K = 2*kept modes <= 64): half the shared memory, twice the
+// resident CTAs per SM to overlap one CTA's stores with another's loads
 
-template <int TM>
+template <int TM, int LM_STAGES>
 __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ L, int ldl, int M, int K,
                                                       const float* __restrict__ R, long long strideRg,
                                                       long long strideRk, float* __restrict__ Out,
@@ -161,20 +163,29 @@ int launch_lmul(const float* L, int ldl, int M, int K, const float* R, long long
                 float* Out, long long strideOg, long long strideOm, int N, int G, cudaStream_t st, int mdiv,
                 long long strideOmLo, long long split_off) {
   if (G <= 0 || M <= 0) return 0;
-  constexpr int SM32 = LM_STAGES * (32 * LDA + KC * TN) * 4, SM64 = LM_STAGES * (64 * LDA + KC * TN) * 4;
+  const int nstg = K <= 2 * KC ? 2 : 4;
+  const int SM32 = nstg * (32 * LDA + KC * TN) * 4, SM64 = nstg * (64 * LDA + KC * TN) * 4;
   // 32-row tiles when M is small or when 64-row tiles would leave most SMs without a CTA
   const long long ctas64 = (long long)G * ceil_div(N, TN) * ceil_div(M, 64);
-  if (M <= 32 || ctas64 < 2 * 148) {
-    dim3 grid(G, ceil_div(N, TN), ceil_div(M, 32));
-    B2_CUDA(cudaFuncSetAttribute(lmul_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM32));
-    B2_CUDA(launch_kernel(lmul_kernel<32>, grid, dim3(128), SM32, st, L, ldl, M, K, R, strideRg, strideRk, Out, strideOg,
-                          strideOm, N, mdiv, strideOmLo, split_off));
+  // ... or when 64-row tiles would spend more than a fifth of their rows on padding that 32-row tiles avoid
+  // (3-D inverse-H: M = 2*70 = 140 -> 192 rows in 64-row tiles, 160 in 32-row tiles)
+  const int pad64 = ceil_div(M, 64) * 64, pad32 = ceil_div(M, 32) * 32;
+  const bool rows32 = M <= 32 || ctas64 < 2 * 148 || (pad32 < pad64 && (pad64 - M) * 5 > M);
+#define B2_LMUL_LAUNCH(TMv, NSv, SMv)                                                                              \
+  do {                                                                                                            \
+    dim3 grid(G, ceil_div(N, TN), ceil_div(M, TMv));                                                              \
+    B2_CUDA(cudaFuncSetAttribute(lmul_kernel<TMv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMv));       \
+    B2_CUDA(launch_kernel(lmul_kernel<TMv, NSv>, grid, dim3(TMv * 4), (size_t)SMv, st, L, ldl, M, K, R, strideRg,   \
+                          strideRk, Out, strideOg, strideOm, N, mdiv, strideOmLo, split_off));                    \
+  } while (0)
+  if (rows32) {
+    if (nstg == 2) B2_LMUL_LAUNCH(32, 2, SM32);
+    else B2_LMUL_LAUNCH(32, 4, SM32);
   } else {
-    dim3 grid(G, ceil_div(N, TN), ceil_div(M, 64));
-    B2_CUDA(cudaFuncSetAttribute(lmul_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64));
-    B2_CUDA(launch_kernel(lmul_kernel<64>, grid, dim3(256), SM64, st, L, ldl, M, K, R, strideRg, strideRk, Out, strideOg,
-                          strideOm, N, mdiv, strideOmLo, split_off));
+    if (nstg == 2) B2_LMUL_LAUNCH(64, 2, SM64);
+    else B2_LMUL_LAUNCH(64, 4, SM64);
   }
+#undef B2_LMUL_LAUNCH
   B2_LAUNCHED("lmul_kernel");
   return 0;
 }
