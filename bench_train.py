@@ -88,7 +88,11 @@ def run_engine(args):
     model = (R.FNO3d(*modes, L, width, s_in, s_out) if ndim == 3 else R.FNO2d(*modes, L, width, s_in, s_out))
     model.load_state_dict(sd)
     model = model.to(dev).train()
-    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)  # train.py:290
+    if args.fused_adam:  # same updates in one pass per parameter (realpdebench_b200/optim.py)
+        from realpdebench_b200.optim import FusedAdam
+        optimizer = FusedAdam(model.parameters(), lr=1e-3)
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)  # train.py:290
     # N > 1: the all-reduce runs under the backward pass (events recorded by b200fno_train_backward); --no-overlap
     # falls back to one bucketed all-reduce after loss.backward()
     overlap = dist is not None and not args.no_overlap
@@ -160,7 +164,7 @@ def run_engine(args):
             "e2e": {"value": world * pts / (e2e_ms * 1e-3), "unit": "field-points/s",
                     "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks.summary(), "phases_ms": phases,
-            "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap, "loss": float(loss.detach())}), flush=True)
+            "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap, "fused_adam": bool(args.fused_adam), "loss": float(loss.detach())}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -173,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="b200fno", choices=["b200fno", "reference"])
     ap.add_argument("--workload", default="fno2d_fsi_64x64_train", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--fused-adam", action="store_true", help="realpdebench_b200.optim.FusedAdam instead of torch's Adam")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of under it")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the bounded CPU sample (--impl reference)")
     args = ap.parse_args()

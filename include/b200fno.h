@@ -202,6 +202,12 @@ int b200fno_train_forward(b200fno_plan_t* plan, int32_t batch, const float* x, f
 int b200fno_train_backward(b200fno_plan_t* plan, int32_t batch, const float* x, const float* dy,
                            const b200fno_grads_t* grads, void* const* grads_ready, void* stream);
 
+/* One Adam update of a flat fp32 tensor in a single pass (torch.optim.Adam as built at train.py:290: betas
+ * (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad; `step` counts from 1).  Complex parameters are passed as
+ * their real view, 2n floats.  param, exp_avg, exp_avg_sq are updated in place. */
+int b200fno_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, int64_t step, void* stream);
+
 /* ---- introspection used by bench.py / tests ------------------------------ */
 /* Kernels launched by this library on this thread since the last reset. */
 int64_t b200fno_launch_count(void);

@@ -1075,4 +1075,13 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   return 0;
 }
 
+int b200fno_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int64_t step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) {
+    set_error("bad argument");
+    return B200FNO_EINVAL;
+  }
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+}
+
 }  // extern "C"

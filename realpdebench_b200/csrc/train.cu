@@ -13,6 +13,8 @@
 //   modes_wgrad / pack_spectral_adj / unpack_spectral_grad    spectral weight gradients
 // fp32 FFMA throughout; reductions accumulate per-CTA partial sums in fp32 and combine them with
 // double (statistics) or float (weight gradients) atomics.
+#include <math.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -698,6 +700,37 @@ int launch_unpack_spectral_grad(const float* dWpk, float* const* corners, int nc
                                                          co, g.Cp, slot_t, slot_h);
     B2_LAUNCHED("unpack_spectral_grad_kernel");
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Fused Adam step (torch.optim.Adam defaults: no weight decay, no amsgrad) in ONE pass over p, g, m, v.
+// Same elementwise formulas, in the same order, as torch's foreach implementation:
+//   m <- m + (1-b1)(g - m);  v <- v*b2 + (1-b2) g*g;  p <- p - step_size * (m / (sqrt(v)/sqrt(bc2) + eps))
+// Complex parameters are passed as their real views (re and im are independent reals, as in torch).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n, float w1,
+                                                   float b2, float w2, float step_size, float bc2_sqrt, float eps) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = fmaf(w1, gi - m[i], m[i]);
+    const float vi = fmaf(w2 * gi, gi, v[i] * b2);
+    m[i] = mi, v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                long long step, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16));
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, 1.0f - beta1, beta2, 1.0f - beta2, (float)((double)lr / bc1),
+                                      (float)sqrt(bc2), eps);
+  B2_LAUNCHED("adam_kernel");
   return 0;
 }
 

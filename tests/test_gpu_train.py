@@ -185,3 +185,43 @@ def test_fsi_fno2d_train_step_vs_torch_on_gpu(R):
     assert abs(loss.item() - loss_ref) < 1e-5 * abs(loss_ref)
     ref32 = {k: v.to(torch.cfloat if v.is_complex() else torch.float).cpu() for k, v in grads_ref.items()}
     check_grads(m, ref32, tol=5e-5)
+
+
+# ---------------------------------------------------------------- fused Adam
+def test_fused_adam_matches_torch_adam(R):
+    """realpdebench_b200.optim.FusedAdam == torch.optim.Adam(lr) as built at train.py:290, over several steps with an
+    LR scheduler, on real / complex parameters of different sizes; and the engine sees the updated weights."""
+    from realpdebench_b200.optim import FusedAdam
+    torch.manual_seed(11)
+    shapes = [(128, 62), (7,), (16, 16, 12, 16), (1, 3, 5)]
+    ps = [torch.randn(*s, device=dev(), dtype=(torch.cfloat if i == 2 else torch.float32)) for i, s in enumerate(shapes)]
+    a = [torch.nn.Parameter(p.clone()) for p in ps]
+    b = [torch.nn.Parameter(p.clone()) for p in ps]
+    oa, ob = torch.optim.Adam(a, lr=1e-2), FusedAdam(b, lr=1e-2)
+    sa = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.5)
+    sb = torch.optim.lr_scheduler.StepLR(ob, step_size=2, gamma=0.5)
+    for it in range(5):
+        gs = [torch.randn_like(p) * (10.0 ** (it - 2)) for p in ps]
+        for x, y, g in zip(a, b, gs):
+            x.grad, y.grad = g.clone(), g.clone()
+        oa.step(), ob.step(), sa.step(), sb.step()
+    for x, y in zip(a, b):
+        assert O.rel_l2(y.detach().cpu(), x.detach().cpu()) < 1e-6
+    # drop-in for the optimiser of the training loop: same losses as torch's Adam on the engine model
+    ctor = (2, 3, 3, 2, 8, (3, 7, 9, 2), (3, 7, 9, 2))
+    torch.manual_seed(12)
+    m1 = R.FNO3d(*ctor).to(dev())
+    m2 = R.FNO3d(*ctor).to(dev())
+    m2.load_state_dict(m1.state_dict())
+    o1, o2 = torch.optim.Adam(m1.parameters(), lr=1e-3), FusedAdam(m2.parameters(), lr=1e-3)
+    x, t = torch.randn(2, *ctor[5], device=dev()), torch.randn(2, *ctor[6], device=dev())
+    l1, l2 = [], []
+    for _ in range(4):
+        for m, o, l in ((m1, o1, l1), (m2, o2, l2)):
+            m.train()
+            o.zero_grad()
+            loss = m.train_loss(x, t).mean()
+            loss.backward()
+            o.step()
+            l.append(loss.item())
+    assert l2 == pytest.approx(l1, rel=1e-4) and l1[-1] < l1[0]
