@@ -71,7 +71,10 @@ class _TrainForward(torch.autograd.Function):
         track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
         rm = [bn.running_mean if track else None for bn in bns]
         rv = [bn.running_var if track else None for bn in bns]
-        momentum = bns[0].momentum if bns[0].momentum is not None else 0.1
+        if any(bn.momentum is None for bn in bns):
+            raise NotImplementedError("b200fno: BatchNorm momentum=None (cumulative average) is not supported; the "
+                                      "reference uses the default momentum 0.1 (fno.py:100)")
+        momentum = bns[0].momentum
         y = module._engine.train_forward(x, sd, key, rm, rv, momentum)
         if track:
             for bn in bns:
