@@ -208,6 +208,17 @@ int b200fno_train_backward(b200fno_plan_t* plan, int32_t batch, const float* x, 
 int b200fno_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, int64_t step, void* stream);
 
+/* ---- evaluation metrics --------------------------------------------------- */
+/* eval_metrics (reference realpdebench/utils/metrics.py:24-131) for ONE chunk of `b` samples (the reference's
+ * batch_size loop, :41, stays with the caller): pred, target [b][t][h][w][channels] device fp32, the first `c` channels
+ * are evaluated.  out13 (device, 13 floats) = rmse, mae, rel_l2_error, r2, ke_error, f_error, low_f_error, mid_f_error,
+ * high_f_error, rel_low_f_error, rel_mid_f_error, rel_high_f_error, freq_error (order of :126-131).  The radial-bin
+ * spectra only use wavenumbers below min(t,h,w)/2 per axis (:75-81), computed as truncated DFTs on the device. */
+size_t b200fno_metrics_workspace_bytes(int32_t b, int32_t t, int32_t h, int32_t w, int32_t channels, int32_t c);
+int b200fno_eval_metrics(const float* pred, const float* target, int32_t b, int32_t t, int32_t h, int32_t w,
+                         int32_t channels, int32_t c, void* workspace, size_t workspace_bytes, float* out13,
+                         void* stream);
+
 /* ---- introspection used by bench.py / tests ------------------------------ */
 /* Kernels launched by this library on this thread since the last reset. */
 int64_t b200fno_launch_count(void);

@@ -1084,4 +1084,20 @@ int b200fno_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
 }
 
+size_t b200fno_metrics_workspace_bytes(int32_t b, int32_t t, int32_t h, int32_t w, int32_t channels, int32_t c) {
+  return metrics_workspace_bytes(b, t, h, w, channels, c);
+}
+
+int b200fno_eval_metrics(const float* pred, const float* target, int32_t b, int32_t t, int32_t h, int32_t w,
+                         int32_t channels, int32_t c, void* workspace, size_t workspace_bytes, float* out13,
+                         void* stream) {
+  if (!pred || !target || !out13) {
+    set_error("null tensor");
+    return B200FNO_EINVAL;
+  }
+  B2_TRY(check_device());
+  return launch_eval_metrics(pred, target, b, t, h, w, channels, c, workspace, workspace_bytes, out13,
+                             (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -203,6 +203,11 @@ int launch_modes_wgrad(const float* S, const float* dO, float* dW, int B, int NM
 int launch_unpack_spectral_grad(const float* dWpk, float* const* corners, int ncorner, const Geom& g, int ci, int co,
                                 int m1, int m2, const int* slot_t, const int* slot_h, cudaStream_t st);
 int launch_pad2d(const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols, cudaStream_t st);
+// ---- evaluation metrics (metrics.cu) ----------------------------------------------
+size_t metrics_workspace_bytes(int b, int t, int h, int w, int ct, int c);
+int launch_eval_metrics(const float* pred, const float* target, int b, int t, int h, int w, int ct, int c, void* ws,
+                        size_t ws_bytes, float* out13, cudaStream_t st);
+
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                 long long step, cudaStream_t st);
 

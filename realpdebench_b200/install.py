@@ -12,7 +12,7 @@ import sys
 _saved = {}
 
 
-def install(wrap_load_model: bool = True) -> None:
+def install(wrap_load_model: bool = True, gpu_metrics: bool = True) -> None:
     import importlib
     engine_fno = importlib.import_module(__package__ + ".fno")
     engine_lm = importlib.import_module(__package__ + ".load_model")  # the submodule, not the re-exported function
@@ -33,6 +33,24 @@ def install(wrap_load_model: bool = True) -> None:
         if not getattr(ref_lm.load_model, "_b200fno_wrapped", False):
             _saved["load_model"] = ref_lm.load_model
             ref_lm.load_model = engine_lm.make_wrapper(ref_lm.load_model)
+    if gpu_metrics:
+        # eval.py:22 / train.py:21 do ``from realpdebench.utils.metrics import eval_metrics`` at import time: replacing
+        # the attribute before they are imported routes the evaluation metrics (utils/metrics.py:24-131, two Python
+        # triple loops on the CPU) to the CUDA kernels.  Without a CUDA device the reference function stays in place.
+        try:
+            import torch
+            import realpdebench.utils.metrics as ref_metrics
+        except Exception:
+            return
+        if torch.cuda.is_available() and not getattr(ref_metrics.eval_metrics, "_b200fno_wrapped", False):
+            from .metrics import eval_metrics as gpu_eval_metrics
+
+            def eval_metrics(pred, target, c, batch_size=None):
+                return gpu_eval_metrics(pred, target, c, batch_size)
+
+            eval_metrics._b200fno_wrapped = True
+            _saved["eval_metrics"] = ref_metrics.eval_metrics
+            ref_metrics.eval_metrics = eval_metrics
 
 
 def uninstall() -> None:
@@ -50,3 +68,6 @@ def uninstall() -> None:
     if "load_model" in _saved:
         import realpdebench.model.load_model as ref_lm
         ref_lm.load_model = _saved.pop("load_model")
+    if "eval_metrics" in _saved:
+        import realpdebench.utils.metrics as ref_metrics
+        ref_metrics.eval_metrics = _saved.pop("eval_metrics")

@@ -18,6 +18,9 @@ What is recorded (torch 2.11.0 CPU):
   train3d.pt     train.py:321-334 executed on the reference FNO3d in .train() mode (loss, gradients after the
                  first backward, losses and state_dict after 3 Adam + StepLR steps); a plain case and one with
                  overlapping spectral corners + T_out = 2*T_in      (python tests/golden/make_golden.py train)
+  metrics.pt     realpdebench/utils/metrics.py eval_metrics run on random fields: whole batch, chunked (batch_size=2,
+                 c=2 of 3 channels), single channel, and a real-data-like case with an all-zero pressure channel
+                                                                    (python tests/golden/make_golden.py metrics)
 """
 import os
 import sys
@@ -114,6 +117,24 @@ def make_train():
                            grads0=grads0, pred0=pred0, sd_final=sd_of(m))
     torch.save(cases, os.path.join(HERE, "train3d.pt"))
     print("train3d.pt", os.path.getsize(os.path.join(HERE, "train3d.pt")))
+
+
+def make_metrics():
+    """eval_metrics (utils/metrics.py:24-131) of the reference itself on small random fields."""
+    torch.set_num_threads(1)
+    import_reference()
+    from realpdebench.utils.metrics import eval_metrics
+    cases = []
+    torch.manual_seed(60)
+    for shape, c, bs in (((3, 8, 10, 12, 3), 3, None), ((5, 12, 8, 14, 3), 2, 2), ((2, 6, 6, 6, 1), 1, None),
+                         ((4, 10, 16, 12, 3), 2, None)):
+        pred, target = torch.randn(*shape), torch.randn(*shape)
+        target = target + 0.5 * torch.sin(torch.arange(shape[1]).float()).reshape(1, -1, 1, 1, 1)
+        pred = target + 0.3 * pred
+        out = eval_metrics(pred, target, c, bs)
+        cases.append(dict(pred=pred, target=target, c=c, batch_size=bs, out=torch.stack([torch.as_tensor(o).float() for o in out])))
+        print("metrics", shape, c, bs, [round(float(o), 5) for o in out])
+    torch.save(cases, os.path.join(HERE, "metrics.pt"))
 
 
 def main():
@@ -214,6 +235,9 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         make_train()
+    elif len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        make_metrics()
     else:
         main()
         make_train()
+        make_metrics()

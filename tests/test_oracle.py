@@ -125,3 +125,11 @@ def test_train_step_restatement_matches_reference(golden, case):
         # reference is not reproducible there even against itself (thread count); running_mean absorbs the bias
         noisy = (k.startswith("convs.") and k.endswith(".bias")) or k.endswith("running_mean")
         assert O.rel_l2(sd[k], v) < (2e-2 if noisy else 1e-5), k
+
+
+# ---------------------------------------------------------------- evaluation metrics (utils/metrics.py:24-131)
+def test_metrics_oracle_matches_reference_golden(golden):
+    from oracle import metrics_oracle as M
+    for case in golden("metrics.pt"):
+        out = torch.stack(M.eval_metrics(case["pred"], case["target"], case["c"], case["batch_size"]))
+        assert torch.allclose(out, case["out"], rtol=1e-5, atol=1e-7), (out, case["out"])
