@@ -9,6 +9,8 @@ Public surface (mirrors the reference names):
 * ``rollout_stream``              - the same over a DataLoader, H2D of batch i+1 overlapped with batch i
 * ``install``                     - registers the above at ``realpdebench.model.fno``
                                     so the unmodified reference scripts use them
+* ``eval_metrics``                - realpdebench/utils/metrics.py:24-131 on the GPU
+* ``dist`` / ``optim``            - gradient all-reduce under the backward pass, fused Adam (training path)
 
 The arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of
 ``include/b200fno.h``; there is no CPU or PyTorch fallback.
@@ -16,8 +18,9 @@ The arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of
 from .fno import FNO2d, FNO3d, SpectralConv2d, SpectralConv3d
 from .install import install, uninstall
 from .load_model import load_model
+from .metrics import eval_metrics
 from .rollout import rollout, rollout_affine, rollout_stream
 
 __all__ = ["FNO3d", "FNO2d", "SpectralConv3d", "SpectralConv2d", "load_model", "rollout", "rollout_affine", "rollout_stream",
-           "install", "uninstall"]
+           "install", "uninstall", "eval_metrics"]
 __version__ = "0.1.0"
