@@ -141,3 +141,60 @@ print("OK")
 ''' % (REF, ROOT, REF)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- training / metrics host logic (no device needed)
+def test_fused_adam_and_metrics_fail_loudly_on_cpu():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    from realpdebench_b200.metrics import eval_metrics
+    from realpdebench_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.randn(4, 3))
+    p.grad = torch.randn(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdam([p], lr=1e-3).step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+    x = torch.randn(2, 4, 4, 4, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        eval_metrics(x, x, 2)
+    with pytest.raises(RuntimeError, match="expects two"):
+        eval_metrics(x, x[:1], 2)
+
+
+def test_gradient_groups_follow_the_backward_order():
+    """dist.OverlappedGradientReducer groups parameters the way b200fno_train_backward finishes them: projection
+    first, then the Fourier layers from last to first, fc0 last - every parameter in exactly one group."""
+    import realpdebench_b200 as R
+    from realpdebench_b200 import dist as D
+    m = R.FNO3d(2, 3, 3, 3, 8, (3, 7, 9, 2), (3, 7, 9, 2))
+    names = [k for k, _ in m.named_parameters()]
+    red = D.OverlappedGradientReducer.__new__(D.OverlappedGradientReducer)
+    red.n_layers = m.n_layers
+    groups = [red._group(names, idx) for idx in [m.n_layers] + list(range(m.n_layers - 1, -1, -1))]
+    groups.append([n for n in names if n.startswith("fc0.")])
+    assert groups[0] == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    assert all(".2." in n for n in groups[1]) and len(groups[1]) == 4 + 2 + 2  # 4 corners, conv w/b, bn w/b
+    flat = [n for g in groups for n in g]
+    assert sorted(flat) == sorted(names) and len(flat) == len(set(flat))
+
+
+def test_install_routes_eval_metrics_only_with_cuda():
+    code = (
+        "import sys, types\n"
+        "for n in ('matplotlib','matplotlib.pyplot','h5py'): sys.modules.setdefault(n, types.ModuleType(n))\n"
+        "sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']\n"
+        "sys.path.insert(0, '/root/reference')\n"
+        "import torch, realpdebench_b200 as R\n"
+        "import realpdebench.utils.metrics as M\n"
+        "orig = M.eval_metrics\n"
+        "R.install()\n"
+        "patched = getattr(M.eval_metrics, '_b200fno_wrapped', False)\n"
+        "assert patched == torch.cuda.is_available(), patched\n"
+        "R.uninstall()\n"
+        "assert M.eval_metrics is orig\n"
+        "print('ok')\n")
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference package not present")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
