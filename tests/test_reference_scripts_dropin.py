@@ -72,3 +72,45 @@ def test_unmodified_train_script_reaches_the_engine(tmp_path):
     assert "Loading model fno with input shape (20, 16, 24, 3)" in text
     assert "Number of parameters: 50357955" in text                 # same parameter count as the reference FNO3d
     assert "Start training on cpu" in text
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour (on a GPU the script would simply evaluate)")
+def test_unmodified_eval_script_reaches_the_engine(tmp_path):
+    """Same for ``realpdebench/eval.py``: checkpoint in the reference's format (model/model.py:14-26) loaded into the
+    engine model by the script itself, then the rollout loop (eval.py:313-319) calls the engine's eval-mode forward."""
+    import yaml
+    sys.path.insert(0, ROOT)
+    import realpdebench_b200 as R
+    root = str(tmp_path / "data")
+    _write_split(root, "numerical", ["101.h5"], 60, 32, 48, ("train",))
+    _write_split(root, "real", ["201.h5"], 240, 16, 24, ("train", "val", "test"))   # horizon = 20 + 10 * 20 frames
+    torch.manual_seed(0)
+    m = R.FNO3d(4, 12, 16, 4, 64, (20, 16, 24, 3), (20, 16, 24, 3))
+    ckpt = str(tmp_path / "model.pth")
+    torch.save({"model_state_dict": m.state_dict(), "train_losses": [1.0], "val_losses": {}, "iteration": 1,
+                "best_iteration": 1, "best_val_loss": 1.0}, ckpt)
+    with open(os.path.join(REF, "realpdebench", "configs", "cylinder", "fno.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg.update(dataset_root=root, num_workers=0, results_path=str(tmp_path / "results"), test_batch_size=2)
+    cfg.pop("checkpoint_path", None)
+    cfg_path = str(tmp_path / "fno.yaml")
+    with open(cfg_path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    code = (
+        "import sys, types, runpy\n"
+        "for n in ('matplotlib','matplotlib.pyplot','h5py'): sys.modules.setdefault(n, types.ModuleType(n))\n"
+        "sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']\n"
+        f"sys.path.insert(0, {REF!r}); sys.path.insert(0, {ROOT!r})\n"
+        "import realpdebench_b200\n"
+        "realpdebench_b200.install()\n"
+        f"sys.argv = ['eval.py', '--config', {cfg_path!r}, '--use_hf_dataset', '--checkpoint_path', {ckpt!r}]\n"
+        "runpy.run_module('realpdebench.eval', run_name='__main__')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    err = r.stderr
+    assert r.returncode != 0
+    assert "no CPU fallback" in err, err[-3000:]
+    assert "realpdebench/eval.py" in err and "model(preds[-1])" in err   # eval.py:314, the rollout loop
+    logs = [os.path.join(dp, f) for dp, _, fs in os.walk(str(tmp_path / "results")) for f in fs if f.endswith(".log")]
+    text = "".join(open(p).read() for p in logs)
+    assert "Number of parameters: 50357955" in text and "loaded." in text and "Start testing on cpu" in text
