@@ -10,6 +10,8 @@ Public surface (mirrors the reference names):
 * ``install``                     - registers the above at ``realpdebench.model.fno``
                                     so the unmodified reference scripts use them
 * ``eval_metrics``                - realpdebench/utils/metrics.py:24-131 on the GPU
+* ``materialize_surrogate``       - realpdebench/data/generate_surrogate_data.py:58-88 for one trajectory
+* ``siblings``                    - the spectral operator behind the MWT / Galerkin ``bixyz,ioxyz->boxyz`` layers
 * ``dist`` / ``optim``            - gradient all-reduce under the backward pass, fused Adam (training path)
 
 The arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of
@@ -20,7 +22,8 @@ from .install import install, uninstall
 from .load_model import load_model
 from .metrics import eval_metrics
 from .rollout import rollout, rollout_affine, rollout_stream
+from .surrogate import materialize_surrogate
 
 __all__ = ["FNO3d", "FNO2d", "SpectralConv3d", "SpectralConv2d", "load_model", "rollout", "rollout_affine", "rollout_stream",
-           "install", "uninstall", "eval_metrics"]
+           "install", "uninstall", "eval_metrics", "materialize_surrogate"]
 __version__ = "0.1.0"

@@ -21,6 +21,11 @@ What is recorded (torch 2.11.0 CPU):
   metrics.pt     realpdebench/utils/metrics.py eval_metrics run on random fields: whole batch, chunked (batch_size=2,
                  c=2 of 3 channels), single channel, and a real-data-like case with an all-zero pressure channel
                                                                     (python tests/golden/make_golden.py metrics)
+  surrogate.pt   data/generate_surrogate_data.py:63-86 (the per-file loop body, source lines exec'd verbatim) on a small
+                 reference FNO3d + GaussianNormalizer and a seeded 9-frame 128 x 128 x 15 trajectory (the script
+                 hard-codes that frame shape); the trajectory is regenerated from its seed, only the output is stored
+  siblings.pt    MWT sparseKernelFT3d / sparseKernelFT2d and the Galerkin SpectralConv3d forwards (modules imported)
+                                                                    (python tests/golden/make_golden.py widening)
 """
 import os
 import sys
@@ -137,6 +142,83 @@ def make_metrics():
     torch.save(cases, os.path.join(HERE, "metrics.pt"))
 
 
+def surrogate_inputs(seed=70, n=9):
+    """Seeded stand-in for ``hf['measured_data']`` (generate_surrogate_data.py:48): [n, 128, 128, 15] float32."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.linspace(0, 1, n).reshape(n, 1, 1, 1)
+    return (torch.randn(n, 128, 128, 15, generator=g) * 0.5 + torch.sin(6.0 * t)).numpy()
+
+
+def make_widening():
+    """the surrogate materialisation loop and the sibling spectral layers, run from the reference."""
+    import importlib.util
+    import numpy as np
+    torch.set_num_threads(1)
+    FNO3d, _, GaussianNormalizer, _, _ = import_reference()
+
+    # ---- generate_surrogate_data.py:63-86, exec'd on a small model ---------
+    with open(os.path.join(REF, "realpdebench", "data", "generate_surrogate_data.py")) as f:
+        lines = f.readlines()
+    assert "for i in range(0, traj_numerical.shape[0]-1, batch_size*step):" in lines[62]
+    assert "pred_list.append(pred_traj_batch.reshape(-1, 128, 128)[[-1]].cpu().numpy())" in lines[85]
+    body = textwrap.dedent("".join(lines[62:86]))
+    step, batch_size, sub_s = 2, 2, 1
+    ctor = (2, 3, 3, 2, 8, (step, 128, 128, 17), (step, 128, 128, 1))
+    torch.manual_seed(71)
+    model = FNO3d(*ctor).eval()
+    randomize_bn(model, 72)
+    g = torch.Generator().manual_seed(73)
+    norm = object.__new__(GaussianNormalizer)
+    norm.device = "cpu"
+    norm.mean_inputs, norm.std_inputs = torch.randn(17, generator=g) * 0.1, torch.rand(17, generator=g) + 0.5
+    norm.mean_targets, norm.std_targets = torch.randn(1, generator=g) * 0.1, torch.rand(1, generator=g) + 0.5
+    traj = surrogate_inputs()
+    ns = dict(torch=torch, np=np, model=model, data_normalizer=norm, traj_numerical=traj, step=step,
+              batch_size=batch_size, sub_s=sub_s, gas_ratio=40, equivalence_ratio=0.85, device="cpu", pred_list=[])
+    exec(body, ns)
+    pred_traj = np.concatenate(ns["pred_list"], axis=0)  # :88
+    print("surrogate", pred_traj.shape, float(pred_traj.sum()), float(np.abs(pred_traj).sum()))
+    torch.save(dict(ctor=ctor, sd=sd_of(model), seed=70, n=9, step=step, batch_size=batch_size, sub_s=sub_s,
+                    gas_ratio=40, equivalence_ratio=0.85,
+                    norm=dict(mean_inputs=norm.mean_inputs, std_inputs=norm.std_inputs,
+                              mean_targets=norm.mean_targets, std_targets=norm.std_targets),
+                    traj_checksum=float(np.abs(traj).sum()), pred_traj=torch.from_numpy(pred_traj)),
+               os.path.join(HERE, "surrogate.pt"))
+
+    # ---- sibling spectral layers -------------------------------------------
+    from realpdebench.model.MWT_libs.models import sparseKernelFT2d, sparseKernelFT3d
+    spec = importlib.util.spec_from_file_location(  # the package __init__ needs IPython; the layer file does not
+        "_galerkin_layers", os.path.join(REF, "realpdebench", "model", "galerkin_transformer_libs", "layers.py"))
+    gl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gl)
+    cases = {}
+    torch.manual_seed(80)
+    for name, k, alpha, c, shape in (("ft3d", 2, 3, 1, (2, 8, 6, 10)),      # all modes kept
+                                     ("ft3d_clipped", 2, 4, 2, (2, 4, 5, 8))):  # l1 = 3 < modes, overlapping corners
+        m = sparseKernelFT3d(k, alpha, c).eval()
+        x = torch.randn(*shape, c, k * k)
+        with torch.no_grad():
+            y = m(x)
+        cases[name] = dict(kind="ft3d", k=k, alpha=alpha, c=c, x=x, y=y, sd=sd_of(m))
+        print("siblings", name, tuple(y.shape), y.sum().item())
+    for name, k, alpha, c, shape in (("ft2d", 3, 5, 1, (2, 16, 20)), ("ft2d_clipped", 2, 6, 1, (3, 8, 10))):
+        m = sparseKernelFT2d(k, alpha, c).eval()
+        x = torch.randn(*shape, c, k * k)
+        with torch.no_grad():
+            y = m(x)
+        cases[name] = dict(kind="ft2d", k=k, alpha=alpha, c=c, x=x, y=y, sd=sd_of(m))
+        print("siblings", name, tuple(y.shape), y.sum().item())
+    m = gl.SpectralConv3d(5, 6, 3, 2, 4).eval()  # (in_dim, out_dim, modes_x, modes_y, modes_t)
+    x = torch.randn(2, 5, 7, 9, 8)
+    with torch.no_grad():
+        y = m(x)
+    cases["galerkin3d"] = dict(kind="galerkin3d", ctor=(5, 6, 3, 2, 4), x=x, y=y, sd=sd_of(m))
+    print("siblings galerkin3d", tuple(y.shape), y.sum().item())
+    torch.save(cases, os.path.join(HERE, "siblings.pt"))
+    for f in ("surrogate.pt", "siblings.pt"):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
 def main():
     torch.set_num_threads(1)
     FNO3d, SpectralConv3d, GaussianNormalizer, RangeNormalizer, mse_loss = import_reference()
@@ -237,7 +319,10 @@ if __name__ == "__main__":
         make_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "metrics":
         make_metrics()
+    elif len(sys.argv) > 1 and sys.argv[1] == "widening":
+        make_widening()
     else:
         main()
         make_train()
         make_metrics()
+        make_widening()
