@@ -39,6 +39,9 @@ WORKLOADS = {
     "fno3d_cylinder_64x128_rollout10": (3, (4, 12, 16), 4, 64, (20, 64, 128, 3), (20, 64, 128, 3), 16, 10),
     # BASELINE.json configs[3] (C4), one sample per GPU
     "fno3d_combustion_128x128x64_rollout10": (3, (4, 16, 16), 4, 64, (64, 128, 128, 4), (64, 128, 128, 4), 1, 10),
+    # the surrogate model of data/generate_surrogate_data.py:27-35, one chunk of 50 independent
+    # 10-frame windows (17 -> 1 channels), one forward (n_autoregressive = 1 is forward + target de-normalisation)
+    "fno3d_surrogate_128x128_c17_forward": (3, (4, 16, 16), 4, 64, (10, 128, 128, 17), (10, 128, 128, 1), 50, 1),
     # BASELINE.json configs[4] (C5): the mode sweep 12 -> 64 at 256^2, single forward, batch 16
     **{f"fno2d_modes{k}_256x256": (2, (k, k), 4, 64, (1, 256, 256, 3), (1, 256, 256, 3), 16, 1)
        for k in (12, 16, 24, 32, 48, 64)},
@@ -210,11 +213,12 @@ def run_reference(args):
 
 def workload_config(wl, n_gpus):
     ndim, modes, L, width, s_in, s_out, B, n_auto = WORKLOADS[wl]
+    act_mb = B * width * (s_in[0] + 6 if ndim == 3 else 1) * (s_in[1] + 6) * (s_in[2] + 6) * 4 / 1e6
     return {"workload": wl, "operator": f"fno{ndim}d", "modes": list(modes), "width": width, "n_layers": L,
             "shape_in": list(s_in), "shape_out": list(s_out), "batch_per_gpu": B, "global_batch": B * n_gpus,
             "n_autoregressive": n_auto, "normalizer": "gaussian", "parallelism": f"batch-sharded x{n_gpus}, "
-            "no data-path collective", "l2_policy": "working set per layer (2 x 278 MB activations) exceeds the "
-            "126 MB L2; no explicit flush"}
+            "no data-path collective", "l2_policy": f"working set per layer (2 x {act_mb:.0f} MB activations) exceeds "
+            "the 126 MB L2; no explicit flush"}
 
 
 def run_engine(args):
