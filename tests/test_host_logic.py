@@ -198,3 +198,26 @@ def test_install_routes_eval_metrics_only_with_cuda():
         pytest.skip("reference package not present")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the engine arm): one JSON line with the
+    contract's keys; under a 2-rank launch only rank 0 works and prints."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True, env=env, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fno_rollout_field_points_per_sec"
+    assert d["unit"] == "field-points/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"] == "fno2d_cylinder_256x512_rollout20" and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0
+    # rank 1 of a multi-rank launch exits 0 without work or output
+    r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, check=True, timeout=120,
+                        env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.stdout.strip() == ""
