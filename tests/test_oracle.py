@@ -133,3 +133,10 @@ def test_metrics_oracle_matches_reference_golden(golden):
     for case in golden("metrics.pt"):
         out = torch.stack(M.eval_metrics(case["pred"], case["target"], case["c"], case["batch_size"]))
         assert torch.allclose(out, case["out"], rtol=1e-5, atol=1e-7), (out, case["out"])
+
+
+def test_reference_rejects_an_empty_batch(golden):
+    """Edge case pinned for the engine's error behaviour: the reference arithmetic raises on a zero-sample batch."""
+    g = golden("kat_a.pt")
+    with pytest.raises(RuntimeError):
+        O.fno3d_forward(g["sd"], g["x"][:0], g["ctor"][6])

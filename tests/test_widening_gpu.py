@@ -134,3 +134,20 @@ def test_routed_sibling_layers_match_reference_golden(golden, case):
     if case == "ft2d":  # with autograd on, the call is the reference forward (the engine operator has no backward)
         m(g["x"].to(dev())).sum().backward()
         assert m.reference_calls == 1 and m.weights1.grad is not None
+
+
+# ---------------------------------------------------------------- edge case: empty batch
+def test_empty_batch_is_an_error_like_the_reference(golden):
+    """The reference fails on a zero-sample batch (its FFT rejects the empty transform with a RuntimeError, checked on
+    the CPU build: 'MKL FFT error ... Inconsistent configuration parameters'); the engine reports a RuntimeError too
+    (C-ABI: batch outside [1, max_batch]) and keeps serving real batches afterwards."""
+    g = golden("kat_a.pt")
+    m = engine_model(g["sd"], g["ctor"])
+    x = g["x"].to(dev())
+    y = m(x)
+    with pytest.raises(RuntimeError):
+        m(x[:0])
+    m2 = engine_model(g["sd"], g["ctor"])  # no plan yet: the descriptor itself is rejected
+    with pytest.raises(RuntimeError):
+        m2(x[:0])
+    assert torch.equal(m(x), y)
