@@ -10,6 +10,7 @@ Public surface (mirrors the reference names):
 * ``install``                     - registers the above at ``realpdebench.model.fno``
                                     so the unmodified reference scripts use them
 * ``eval_metrics``                - realpdebench/utils/metrics.py:24-131 on the GPU
+* ``python -m realpdebench_b200.run {train,eval,train_surrogate} ...`` - ``install()`` + the unmodified reference script
 * ``materialize_surrogate``       - realpdebench/data/generate_surrogate_data.py:58-88 for one trajectory
 * ``siblings``                    - the spectral operator behind the MWT / Galerkin ``bixyz,ioxyz->boxyz`` layers
 * ``dist`` / ``optim``            - gradient all-reduce under the backward pass, fused Adam (training path)

@@ -1,5 +1,5 @@
 """Drop-in at the script level (as far as a CPU box can take it): the UNMODIFIED reference
-``realpdebench/train.py`` is run (``runpy``, ``__main__``) on a synthetic HF-Arrow dataset written in the reference's own
+``realpdebench/train.py`` is run (``python -m realpdebench_b200.run train ...``) on a synthetic HF-Arrow dataset written in the reference's own
 on-disk format (``data/fluid_hf_dataset.py:130-180``: ``{root}/{scenario}/hf_dataset/{real,numerical}`` +
 ``{split}_index_{type}.json``) with the reference's ``configs/cylinder/fno.yaml`` (only ``dataset_root``, worker and batch
 counts changed in a temporary copy).  After ``realpdebench_b200.install()`` the script must build the ENGINE model through
@@ -36,6 +36,14 @@ def _write_split(root, dtype, sims, t, h, w, splits):
             json.dump(idx, f)
 
 
+def _launch(tmp_path, script, *args):
+    """``python -m realpdebench_b200.run <script> ...``: the launcher installs the engine and runs the unmodified
+    reference script; matplotlib / h5py (absent from this image, unused by the FNO path) are stubbed."""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, REF, os.environ.get("PYTHONPATH", "")]))
+    cmd = [sys.executable, "-m", "realpdebench_b200.run", "--stub", "matplotlib.pyplot,h5py", script, *args]
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=600, env=env)
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour (on a GPU the script would simply train)")
 def test_unmodified_train_script_reaches_the_engine(tmp_path):
@@ -51,16 +59,7 @@ def test_unmodified_train_script_reaches_the_engine(tmp_path):
     cfg_path = str(tmp_path / "fno.yaml")
     with open(cfg_path, "w") as f:
         yaml.safe_dump(cfg, f)
-    code = (
-        "import sys, types, runpy\n"
-        "for n in ('matplotlib','matplotlib.pyplot','h5py'): sys.modules.setdefault(n, types.ModuleType(n))\n"
-        "sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']\n"
-        f"sys.path.insert(0, {REF!r}); sys.path.insert(0, {ROOT!r})\n"
-        "import realpdebench_b200\n"
-        "realpdebench_b200.install()\n"
-        f"sys.argv = ['train.py', '--config', {cfg_path!r}, '--use_hf_dataset']\n"
-        "runpy.run_module('realpdebench.train', run_name='__main__')\n")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    r = _launch(tmp_path, "train", "--config", cfg_path, "--use_hf_dataset")
     err = r.stderr
     assert r.returncode != 0
     assert "no CPU fallback" in err, err[-3000:]                    # the engine was called ...
@@ -97,16 +96,7 @@ def test_unmodified_eval_script_reaches_the_engine(tmp_path):
     cfg_path = str(tmp_path / "fno.yaml")
     with open(cfg_path, "w") as f:
         yaml.safe_dump(cfg, f)
-    code = (
-        "import sys, types, runpy\n"
-        "for n in ('matplotlib','matplotlib.pyplot','h5py'): sys.modules.setdefault(n, types.ModuleType(n))\n"
-        "sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']\n"
-        f"sys.path.insert(0, {REF!r}); sys.path.insert(0, {ROOT!r})\n"
-        "import realpdebench_b200\n"
-        "realpdebench_b200.install()\n"
-        f"sys.argv = ['eval.py', '--config', {cfg_path!r}, '--use_hf_dataset', '--checkpoint_path', {ckpt!r}]\n"
-        "runpy.run_module('realpdebench.eval', run_name='__main__')\n")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    r = _launch(tmp_path, "eval", "--config", cfg_path, "--use_hf_dataset", "--checkpoint_path", ckpt)
     err = r.stderr
     assert r.returncode != 0
     assert "no CPU fallback" in err, err[-3000:]
@@ -114,3 +104,13 @@ def test_unmodified_eval_script_reaches_the_engine(tmp_path):
     logs = [os.path.join(dp, f) for dp, _, fs in os.walk(str(tmp_path / "results")) for f in fs if f.endswith(".log")]
     text = "".join(open(p).read() for p in logs)
     assert "Number of parameters: 50357955" in text and "loaded." in text and "Start testing on cpu" in text
+
+
+def test_launcher_usage_and_missing_reference(tmp_path):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "realpdebench_b200.run", "plot"], capture_output=True, text=True, env=env,
+                       cwd=str(tmp_path))
+    assert r.returncode != 0 and "usage: python -m realpdebench_b200.run" in r.stderr
+    r = subprocess.run([sys.executable, "-m", "realpdebench_b200.run", "eval"], capture_output=True, text=True, env=env,
+                       cwd=str(tmp_path))
+    assert r.returncode != 0 and "reference package 'realpdebench' is not importable" in r.stderr
