@@ -167,6 +167,17 @@ class GaussianStats:
                y * self.std_targets[..., :c2] + self.mean_targets[..., :c2]
 
 
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_sample(wl, steps, warmup, n_auto_sample=1, batch=1):
     """The oracle port (torch CPU ops == the reference's arithmetic) on a bounded sample of the workload."""
     from oracle import fno_oracle as O
@@ -188,7 +199,8 @@ def cpu_reference_sample(wl, steps, warmup, n_auto_sample=1, batch=1):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
-    return {"value": pts / (ms * 1e-3), "unit": "field-points/s", "cores": cores, "kind": "port",
+    return {"value": pts / (ms * 1e-3), "unit": "field-points/s", "cores": cores, "cpu_model": cpu_model_name(),
+            "kind": "port",
             "sample": f"oracle/fno_oracle.py rollout, batch {batch}, {n_auto_sample} autoregressive step(s) of "
                       f"{wl}, mean of {steps} run(s) after {warmup} warm-up, torch {torch.__version__} CPU "
                       f"{cores} threads", "ms_per_sample": ms}
@@ -205,7 +217,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_sample"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(wl, args.gpus), "cpu_baseline": {k: base[k] for k in
-                                                                        ("value", "unit", "cores", "kind", "sample")},
+                                                                        ("value", "unit", "cores", "cpu_model", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "field-points/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -345,7 +357,7 @@ def run_engine(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again
         cpu_baseline = cpu_reference_sample(wl, 2, 1)
-        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "cpu_model", "kind", "sample")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "field-points/s", "n_gpus": world, "steps": args.steps,

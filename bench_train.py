@@ -62,7 +62,8 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     pts = B * s_out[0] * s_out[1] * s_out[2]
     v = pts / (ms * 1e-3)
-    base = {"value": v, "unit": "field-points/s", "cores": cores, "kind": "port",
+    from bench import cpu_model_name
+    base = {"value": v, "unit": "field-points/s", "cores": cores, "cpu_model": cpu_model_name(), "kind": "port",
             "sample": f"oracle/fno_oracle.py train_steps (fwd + autograd bwd + Adam), batch {B} of {args.workload}, "
                       f"mean of {len(times)} step(s) after 1 warm-up, torch {torch.__version__} CPU {cores} threads"}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "field-points/s", "n_gpus": args.gpus,
