@@ -139,6 +139,40 @@ def build_state(ndim, modes, n_layers, width, s_in, s_out):
     return sd
 
 
+def randomize_bn_(module, seed=123):
+    """The BN recipe of build_state (oracle.randomize_bn, KAT-A of SURVEY section 4) applied to a module in place:
+    same generator, same draw order (mean, var, weight, bias per layer)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for bn in module.bns:
+            c = bn.weight.numel()
+            bn.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+            bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+            bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+            bn.bias.copy_(torch.randn(c, generator=g) * 0.1)
+
+
+def build_model(R, ndim, modes, n_layers, width, s_in, s_out):
+    """Engine arm: the module's OWN initialisation under seed 0 (bit-identical to the reference's / the oracle's,
+    tests/test_host_logic.py) + the BN recipe above - the same weights build_state() gives the CPU arm, without
+    importing anything from oracle/ on the product path."""
+    torch.manual_seed(0)
+    model = (R.FNO3d(*modes, n_layers, width, s_in, s_out) if ndim == 3
+             else R.FNO2d(*modes, n_layers, width, s_in, s_out))
+    randomize_bn_(model)
+    return model
+
+
+def oracle_loss_check(wl):
+    """Oracle value of the normalised rollout loss for rank 0's seeded batch (tests/golden/make_bench_loss.py)."""
+    p = os.path.join(ROOT, "tests", "golden", "bench_loss_check.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(wl)
+    except OSError:
+        return None
+
+
 def synthetic_stats(c_in, c_out):
     g = torch.Generator().manual_seed(4321)
     mi, si = torch.randn(c_in, generator=g) * 0.1, torch.rand(c_in, generator=g) + 0.5
@@ -257,10 +291,7 @@ def run_engine(args):
         B = args.batch
     if args.n_auto:
         n_auto = args.n_auto
-    sd = build_state(ndim, modes, L, width, s_in, s_out)
-    model = (R.FNO3d(*modes, L, width, s_in, s_out) if ndim == 3 else R.FNO2d(*modes, L, width, s_in, s_out))
-    model.load_state_dict(sd)
-    model = model.to(dev).eval()
+    model = build_model(R, ndim, modes, L, width, s_in, s_out).to(dev).eval()
     if args.engine_impl != "auto":
         model.set_impl(args.engine_impl)
     norm = GaussianStats(dev, **synthetic_stats(s_in[-1], s_out[-1]))
@@ -327,31 +358,47 @@ def run_engine(args):
              "frac_of_hbm_peak": alg_bytes_step / (ms_step * 1e-3) / 1e9 / peak}
 
     # ---------------- end-to-end arm: public API with host buffers ----------------
-    def e2e_step():
-        return R.rollout(model, norm, x_host, tgt_host, n_auto, unmeasured_c=0)
+    # eval.py:296-343 per batch: input + target from pinned host memory (H2D inside the timed region), normalise,
+    # N-step rollout, normalised loss, de-normalise, and the prediction BACK on the host (eval.py:342 pred.cpu()).
+    # rollout_stream pipelines three streams: H2D of batch i+1 | rollout of batch i | D2H of prediction i-1.
+    def e2e_run(n):
+        tot = 0.0
+        for p_host, _, l in R.rollout_stream(model, norm, ((x_host, tgt_host) for _ in range(n)), n_auto,
+                                             unmeasured_c=0, to_host=not args.e2e_no_d2h):
+            tot += l
+        return tot, p_host
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     f0.record()
-    loss = 0.0
-    # every step copies its own input + target from pinned host memory (H2D inside the timed region) and
-    # reads the normalised loss back; rollout_stream overlaps the copy of step i+1 with the rollout of step i
-    for _, _, l in R.rollout_stream(model, norm, ((x_host, tgt_host) for _ in range(e2e_steps)), n_auto,
-                                    unmeasured_c=0):
-        loss += l
+    loss, p_host = e2e_run(e2e_steps)
     f1.record()
     barrier()
     e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3 / e2e_steps
     e2e_ms = reduce_max(max(f0.elapsed_time(f1) / e2e_steps, e2e_wall_ms))
+    d2h = 4 if args.e2e_no_d2h else p_host.numel() * 4 + 4
     e2e = {"value": world * pts_per_step / (e2e_ms * 1e-3), "unit": "field-points/s",
-           "h2d_bytes_per_step": x_host.numel() * 4 + tgt_host.numel() * 4, "d2h_bytes_per_step": 4,
+           "h2d_bytes_per_step": x_host.numel() * 4 + tgt_host.numel() * 4, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "api": "realpdebench_b200.rollout_stream(model, data_normalizer, host_batches, N_autoregressive) "
-                  "(= rollout() per batch with the next batch's H2D staged on a copy stream)"}
+           "result_on_host": "de-normalised prediction tensor (pinned ring buffer) + normalised loss"
+           if not args.e2e_no_d2h else "normalised loss only",
+           "api": "realpdebench_b200.rollout_stream(model, data_normalizer, host_batches, N_autoregressive, "
+                  "to_host=True): H2D of batch i+1, rollout of batch i and D2H of prediction i-1 on three streams"}
+    # rank 0's seeded batch has an oracle-derived loss (tests/golden/bench_loss_check.json): the whole timed path
+    # (copies, normalisation, 20 fed-back steps on the tensor-core kernels, loss) must reproduce it
+    loss_check = loss / e2e_steps
+    want = oracle_loss_check(wl) if not (args.batch or args.n_auto) else None
+    loss_ok = None
+    if want is not None:
+        loss_ok = abs(loss_check - want["normalized_loss"]) <= 1e-5 * abs(want["normalized_loss"])
+    if not args.e2e_no_d2h:  # the host copy of the prediction is the device result, bit for bit
+        dev_pred = R.rollout(model, norm, x_host, tgt_host, n_auto, unmeasured_c=0)[0]
+        host_ok = bool(torch.equal(dev_pred.cpu(), p_host))
+    else:
+        host_ok = None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -366,12 +413,17 @@ def run_engine(args):
                 "impl": "b200fno", "engine_impl": args.engine_impl, "e2e": e2e, "host_numa_cpulist": numa, "gpu_launches": launches,
                 "clocks": clocks.summary(), "roofline": roofline, "whole_step": whole,
                 "stages_ms_per_rollout": {k: round(v["ms"], 4) for k, v in stages.items()},
-                "cpu_baseline": cpu_baseline, "normalized_loss_check": loss / e2e_steps}
+                "cpu_baseline": cpu_baseline, "normalized_loss_check": loss_check,
+                "normalized_loss_oracle": want["normalized_loss"] if want else None, "normalized_loss_ok": loss_ok,
+                "host_prediction_equals_device": host_ok, "stage_impls": eng.stage_impls()}
         if args.batch or args.n_auto:
             line["config"]["batch_per_gpu"], line["config"]["n_autoregressive"] = B, n_auto
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and (loss_ok is False or host_ok is False):
+        raise SystemExit(f"bench.py: parity check failed (normalized loss {loss_check!r} vs oracle "
+                         f"{want and want['normalized_loss']!r}; host prediction == device: {host_ok})")
 
 
 def main():
@@ -386,6 +438,8 @@ def main():
     ap.add_argument("--n-auto", type=int, default=0, help="override rollout length (not the headline config)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-no-d2h", action="store_true",
+                    help="round-1 e2e (only the loss scalar returns to the host); default returns the prediction")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,7 +23,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-from bench import ClockSampler, build_state  # noqa: E402
+from bench import ClockSampler, build_model, build_state  # noqa: E402
 
 WORKLOADS = {
     # name: (ndim, modes, n_layers, width, shape_in, shape_out, batch per GPU)
@@ -85,10 +85,7 @@ def run_engine(args):
     dist = D.init("nccl", dev)
     ndim, modes, L, width, s_in, s_out, B = WORKLOADS[args.workload]
     B = args.batch or B
-    sd = build_state(ndim, modes, L, width, s_in, s_out)
-    model = (R.FNO3d(*modes, L, width, s_in, s_out) if ndim == 3 else R.FNO2d(*modes, L, width, s_in, s_out))
-    model.load_state_dict(sd)
-    model = model.to(dev).train()
+    model = build_model(R, ndim, modes, L, width, s_in, s_out).to(dev).train()
     if args.fused_adam:  # same updates in one pass per parameter (realpdebench_b200/optim.py)
         from realpdebench_b200.optim import FusedAdam
         optimizer = FusedAdam(model.parameters(), lr=1e-3)
@@ -166,8 +163,16 @@ def run_engine(args):
                     "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks.summary(), "phases_ms": phases,
             "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap, "fused_adam": bool(args.fused_adam), "loss": float(loss.detach())}), flush=True)
+    # a step that produced a non-finite loss or parameter is not a measurement: fail loudly on every rank
+    finite = bool(torch.isfinite(loss.detach())) and all(
+        bool(torch.isfinite(torch.view_as_real(p) if p.is_complex() else p).all()) for p in model.parameters())
     if dist is not None:
+        flag = torch.tensor([0.0 if finite else 1.0], device=dev)
+        dist.all_reduce(flag)
+        finite = float(flag.item()) == 0.0
         dist.destroy_process_group()
+    if not finite:
+        raise SystemExit("bench_train.py: non-finite loss or parameter after the timed steps - the numbers above are void")
 
 
 def main():

@@ -22,7 +22,7 @@ SYMBOLS = (
     "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
     "b200fno_timing_collect", "b200fno_selftest_umma", "b200fno_selftest_mma_rate",
     "b200fno_train_workspace_bytes", "b200fno_train_bind", "b200fno_train_forward", "b200fno_train_backward",
-    "b200fno_adam_step", "b200fno_metrics_workspace_bytes", "b200fno_eval_metrics",
+    "b200fno_adam_step", "b200fno_metrics_workspace_bytes", "b200fno_eval_metrics", "b200fno_plan_stage_impl",
 )
 
 
@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
     L.b200fno_metrics_workspace_bytes.argtypes = [i32] * 6
     L.b200fno_eval_metrics.restype = C.c_int
     L.b200fno_eval_metrics.argtypes = [vp, vp] + [i32] * 6 + [vp, sz, vp, vp]
+    L.b200fno_plan_stage_impl.restype = C.c_int
+    L.b200fno_plan_stage_impl.argtypes = [vp, i32]
     L.b200fno_algorithmic_bytes.restype = C.c_double
     L.b200fno_algorithmic_bytes.argtypes = [vp, i32]
     if L.b200fno_abi_version() != ABI_VERSION:

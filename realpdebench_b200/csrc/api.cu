@@ -821,6 +821,26 @@ int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_
   return n;
 }
 
+int b200fno_plan_stage_impl(const b200fno_plan_t* p, int32_t stage) {
+  if (!p || !p->ws || stage < 0 || stage >= ST_COUNT) {
+    set_error("b200fno_plan_stage_impl: bound plan and a stage in [0, %d) required", (int)ST_COUNT);
+    return B200FNO_EINVAL;
+  }
+  const Tables& tb = p->tab;
+  switch (stage) {
+    case ST_LIFT: return p->use_tc_lift;
+    case ST_FWD_W: return p->use_tc && p->use_tc_fwdw;
+    case ST_FWD_H: return p->use_tc && p->use_tc_tmul && tb.tm_fwdH.ok;
+    case ST_FWD_T: return p->use_tc && p->use_tc_tmul && tb.tm_fwdT.ok;
+    case ST_MODES: return 0;
+    case ST_INV_T: return p->use_tc && p->use_tc_tmul && tb.tm_invT.ok;
+    case ST_INV_H: return p->use_tc && p->use_tc_tmul && tb.tm_invH.ok;
+    case ST_LAYER: return p->use_tc;
+    case ST_PROJ: return p->use_tc_proj;
+  }
+  return 0;
+}
+
 double b200fno_algorithmic_bytes(const b200fno_plan_t* p, int32_t batch) {
   if (!p) return 0.0;
   const b200fno_desc_t& d = p->d;

@@ -32,31 +32,108 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None):
     return dist
 
 
-def bind_to_gpu_numa(local_rank: int) -> Optional[str]:
-    """Pin this process to the CPUs that are NUMA-local to GPU ``local_rank`` (from the PCI device's
-    ``local_cpulist`` in sysfs) so that pinned host buffers allocated afterwards are first-touched on the
-    GPU's socket and H2D copies do not cross the inter-socket link.  Returns the cpulist applied, or None when
-    the topology is not exposed (containers without sysfs PCI entries) - never raises."""
+def _parse_cpulist(cpulist: str) -> set:
+    cpus = set()
+    for part in cpulist.strip().split(","):
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def _pci_address(index: int) -> Optional[str]:
+    """'dddd:bb:dd.f' of CUDA device ``index`` (torch device properties, else nvidia-smi)."""
     try:
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.6
-        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
-        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
-        with open(path) as f:
-            cpulist = f.read().strip()
-        cpus = set()
-        for part in cpulist.split(","):
-            if "-" in part:
-                lo, hi = part.split("-")
-                cpus.update(range(int(lo), int(hi) + 1))
-            elif part:
-                cpus.add(int(part))
-        allowed = os.sched_getaffinity(0)
-        cpus &= allowed
-        if not cpus or cpus == allowed:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return cpulist
+        pr = torch.cuda.get_device_properties(index)
+        if hasattr(pr, "pci_bus_id"):
+            return f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
+    except Exception:
+        pass
+    try:
+        import subprocess
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        r = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                           text=True, timeout=20)
+        rows = [l.split(",") for l in r.stdout.strip().splitlines()]
+        ids = {int(a): b.strip().lower() for a, b in rows}
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        addr = ids[phys]  # nvidia-smi prints an 8-digit domain
+        dom, rest = addr.split(":", 1)
+        return f"{int(dom, 16):04x}:{rest}"
+    except Exception:
+        return None
+
+
+def gpu_host_locality(index: int) -> dict:
+    """PCI address, NUMA node and NUMA-local CPUs of CUDA device ``index`` as far as sysfs exposes them."""
+    info = {"gpu": index, "pci": _pci_address(index), "numa_node": None, "local_cpulist": None}
+    if info["pci"]:
+        base = f"/sys/bus/pci/devices/{info['pci']}"
+        try:
+            with open(base + "/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+        except (OSError, ValueError):
+            pass
+        try:
+            with open(base + "/local_cpulist") as f:
+                info["local_cpulist"] = f.read().strip()
+        except OSError:
+            pass
+    if info["numa_node"] is not None and info["numa_node"] >= 0 and not info["local_cpulist"]:
+        try:
+            with open(f"/sys/devices/system/node/node{info['numa_node']}/cpulist") as f:
+                info["local_cpulist"] = f.read().strip()
+        except OSError:
+            pass
+    return info
+
+
+_MPOL_DEFAULT, _MPOL_PREFERRED, _MPOL_BIND = 0, 1, 2
+
+
+def set_memory_policy(node: Optional[int], strict: bool = False) -> bool:
+    """``set_mempolicy(2)`` for the calling thread: pages touched / pinned afterwards come from NUMA node ``node``
+    (MPOL_PREFERRED, or MPOL_BIND when ``strict``); ``None`` restores the default first-touch policy.  This works when
+    the container's cpuset confines the CPUs to one socket but not the memory - the case where CPU affinity alone
+    cannot place a pinned buffer next to the GPU.  Returns False when the kernel refuses (never raises)."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        SYS_set_mempolicy = 238  # x86_64
+        if os.uname().machine == "aarch64":
+            SYS_set_mempolicy = 237
+        if node is None or node < 0:
+            return libc.syscall(SYS_set_mempolicy, _MPOL_DEFAULT, None, 0) == 0
+        nbits = 1024
+        mask = (ctypes.c_ulong * (nbits // (8 * ctypes.sizeof(ctypes.c_ulong))))()
+        w = 8 * ctypes.sizeof(ctypes.c_ulong)
+        mask[node // w] |= 1 << (node % w)
+        mode = _MPOL_BIND if strict else _MPOL_PREFERRED
+        return libc.syscall(SYS_set_mempolicy, mode, mask, nbits + 1) == 0
+    except Exception:
+        return False
+
+
+def bind_to_gpu_numa(local_rank: int) -> Optional[str]:
+    """Place this process next to GPU ``local_rank``: (1) restrict its CPUs to the GPU's NUMA-local ones when they
+    are a proper subset of what the process may use, (2) prefer the GPU's NUMA node for memory allocated from now
+    on (the pinned staging buffers), so H2D copies do not cross the inter-socket link.  Returns a description of what
+    was applied, or None when the topology is not exposed - never raises."""
+    try:
+        info = gpu_host_locality(local_rank)
+        applied = []
+        if info["local_cpulist"]:
+            allowed = os.sched_getaffinity(0)
+            cpus = _parse_cpulist(info["local_cpulist"]) & allowed
+            if cpus and cpus != allowed:
+                os.sched_setaffinity(0, cpus)
+                applied.append(f"cpus {info['local_cpulist']}")
+        node = info["numa_node"]
+        if node is not None and node >= 0 and set_memory_policy(node):
+            applied.append(f"mempolicy preferred node{node}")
+        return ", ".join(applied) if applied else None
     except Exception:
         return None
 
@@ -98,6 +175,18 @@ def _real_view(t: torch.Tensor) -> torch.Tensor:
     return torch.view_as_real(t) if t.is_complex() else t
 
 
+def _broadcast_into(module, tensors, dist, src: int) -> None:
+    """Broadcast ``tensors`` of ``module`` from rank ``src`` in place.  The writes go through ``.data`` (leaf
+    parameters that require grad cannot be written in place otherwise), which does not advance the tensors' version
+    counters - so the engine's packed copy (keyed by data_ptr / version / ``_stats_epoch``) is invalidated
+    explicitly: the next forward on every rank re-packs from the synchronised values."""
+    if dist is None:
+        return
+    for t in tensors:
+        dist.broadcast(_real_view(t.data), src=src)
+    module._stats_epoch = getattr(module, "_stats_epoch", 0) + 1
+
+
 class GradientAllReducer:
     """Average parameter gradients over the ranks after ``loss.backward()`` (train.py:329), before
     ``optimizer.step()`` (train.py:333) - what DDP would do to the reference's single-GPU step.
@@ -127,16 +216,11 @@ class GradientAllReducer:
 
     def sync_parameters(self, src: int = 0) -> None:
         """Broadcast rank ``src``'s parameters and buffers (start of training / after loading a checkpoint)."""
-        if self.dist is None:
-            return
-        for t in list(self.module.parameters()) + list(self.module.buffers()):
-            self.dist.broadcast(_real_view(t.data), src=src)
+        _broadcast_into(self.module, list(self.module.parameters()) + list(self.module.buffers()), self.dist, src)
 
     def sync_buffers(self, src: int = 0) -> None:
-        if self.dist is None:
-            return
-        for t in self.module.buffers():
-            self.dist.broadcast(t.data, src=src)
+        """DDP's buffer broadcast: rank ``src``'s BatchNorm running statistics to every rank."""
+        _broadcast_into(self.module, list(self.module.buffers()), self.dist, src)
 
     @torch.no_grad()
     def __call__(self) -> int:
@@ -193,10 +277,10 @@ class OverlappedGradientReducer:
         self.module._grad_sync = None
 
     def sync_parameters(self, src: int = 0) -> None:
-        if self.dist is None:
-            return
-        for t in list(self.module.parameters()) + list(self.module.buffers()):
-            self.dist.broadcast(_real_view(t.data), src=src)
+        _broadcast_into(self.module, list(self.module.parameters()) + list(self.module.buffers()), self.dist, src)
+
+    def sync_buffers(self, src: int = 0) -> None:
+        _broadcast_into(self.module, list(self.module.buffers()), self.dist, src)
 
     def _group(self, names, idx):
         L = self.n_layers
@@ -205,10 +289,15 @@ class OverlappedGradientReducer:
         tag = f".{idx}."
         return [n for n in names if tag in n and n.startswith(("spectral_convs.", "convs.", "bns."))]
 
-    def backward_and_reduce(self, engine, x, dy, params: dict) -> dict:
+    def backward_and_reduce(self, engine, x, dy, params: dict, seq=None) -> dict:
         dist, L = self.dist, self.n_layers
         cur = torch.cuda.current_stream(x.device)
-        grads = engine.train_backward(x, dy, params, ready_events=[e.cuda_event for e in self.events])
+        handles = [e.cuda_event for e in self.events]
+        if not all(handles):
+            raise RuntimeError("OverlappedGradientReducer: a gradient-ready event has no cudaEvent_t handle")
+        grads = engine.train_backward(x, dy, params, ready_events=handles, seq=seq)
+        if os.environ.get("B200FNO_REDUCER_SYNC"):  # race probe (profiles/diag_train.py): no overlap at all
+            torch.cuda.synchronize(x.device)
         done = torch.cuda.Event()
         done.record(cur)  # fc0 gradients (and everything else) final
         works, total = [], 0

@@ -6,6 +6,7 @@ every kernel is launched by ``libb200fno.so``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -40,6 +41,7 @@ class FNOEngine:
         self._ws = self._packed = self._train_ws = None
         self._weights_key = None
         self._keepalive: List[torch.Tensor] = []
+        self._train_seq = 0  # id of the train-mode forward whose activations the training workspace holds
 
     # -- plan management ------------------------------------------------------
     def _destroy(self):
@@ -189,18 +191,33 @@ class FNOEngine:
         with torch.cuda.device(x.device):
             check(_capi.lib().b200fno_train_forward(self._plan, x.shape[0], x.data_ptr(), y.data_ptr(), rm, rv,
                                                     float(momentum), stream))
+        self._train_seq += 1
         return y
 
+    @property
+    def train_seq(self) -> int:
+        return self._train_seq
+
     def train_backward(self, x: torch.Tensor, dy: torch.Tensor, params: dict,
-                       ready_events: Optional[Sequence[int]] = None) -> dict:
+                       ready_events: Optional[Sequence[int]] = None, seq: Optional[int] = None) -> dict:
         """Parameter gradients of the last ``train_forward`` in the reference layout.
         ``params``: name -> parameter tensor (reference state_dict names); returns name -> gradient tensor.
         ``ready_events``: optional ``n_layers + 1`` raw ``cudaEvent_t`` handles recorded when each gradient group
         is final (see ``b200fno_train_backward``)."""
         _require_cuda(dy, "output gradient")
+        if seq is not None and seq != self._train_seq:
+            # the training workspace holds the activations of ONE forward (b200fno.h: "one forward outstanding per
+            # plan"); a second train-mode forward before this backward has overwritten them
+            raise RuntimeError(
+                f"b200fno: backward of train-mode forward #{seq} requested, but the engine's training workspace holds "
+                f"forward #{self._train_seq}: only one train-mode forward may be outstanding per model (run "
+                "forward -> backward pairs, e.g. accumulate gradients over separate loss.backward() calls)")
         x, dy = x.contiguous(), dy.contiguous()
         ncorner = 4 if self.ndim == 3 else 2
-        grads = {k: torch.empty_like(v) for k, v in params.items()}
+        if os.environ.get("B200FNO_POISON_GRADS"):  # debugging aid: a never-written gradient element stays NaN
+            grads = {k: torch.full_like(v, float("nan")) for k, v in params.items()}
+        else:
+            grads = {k: torch.empty_like(v) for k, v in params.items()}
 
         def ptr(name):
             g = grads[name]
@@ -227,6 +244,16 @@ class FNOEngine:
     def resolved_impl(self) -> str:
         """'tc' if the tcgen05 layer kernel is in use for this shape, else 'simt' (plan must exist)."""
         return "tc" if _capi.lib().b200fno_plan_get_impl(self._plan) == _capi.IMPL_TC else "simt"
+
+    def stage_impls(self) -> dict:
+        """stage name -> 'tc' | 'simt' for the bound plan (b200fno_plan_stage_impl)."""
+        out = {}
+        for i, s in enumerate(_capi.STAGES):
+            r = _capi.lib().b200fno_plan_stage_impl(self._plan, i)
+            if r < 0:
+                check(r)
+            out[s] = "tc" if r else "simt"
+        return out
 
     def timing(self, on: bool) -> None:
         """Bracket every stage launch with CUDA events (bench.py's per-kernel roofline numbers)."""

@@ -83,6 +83,7 @@ class _TrainForward(torch.autograd.Function):
             module._stats_epoch = getattr(module, "_stats_epoch", 0) + 1
         ctx.module, ctx.names, ctx.x = module, names, x
         ctx.params = params
+        ctx.seq = module._engine.train_seq  # the workspace now holds THIS forward's activations
         return y
 
     @staticmethod
@@ -91,9 +92,9 @@ class _TrainForward(torch.autograd.Function):
         params = dict(zip(ctx.names, ctx.params))
         sync = getattr(ctx.module, "_grad_sync", None)  # dist.OverlappedGradientReducer: all-reduce under the backward
         if sync is not None:
-            grads = sync.backward_and_reduce(ctx.module._engine, ctx.x, dy, params)
+            grads = sync.backward_and_reduce(ctx.module._engine, ctx.x, dy, params, seq=ctx.seq)
         else:
-            grads = ctx.module._engine.train_backward(ctx.x, dy, params)
+            grads = ctx.module._engine.train_backward(ctx.x, dy, params, seq=ctx.seq)
         out = tuple(grads[n] if nd else None for n, nd in zip(ctx.names, need))
         return (None, None, None) + out
 

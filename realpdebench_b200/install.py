@@ -46,7 +46,10 @@ def install(wrap_load_model: bool = True, gpu_metrics: bool = True) -> None:
             from .metrics import eval_metrics as gpu_eval_metrics
 
             def eval_metrics(pred, target, c, batch_size=None):
-                return gpu_eval_metrics(pred, target, c, batch_size)
+                # the reference returns its scalars on ``target.device`` (utils/metrics.py:36); train.py:376-416
+                # torch.saves them into checkpoints, so host inputs must give host results
+                out = gpu_eval_metrics(pred, target, c, batch_size)
+                return tuple(v.to(target.device) for v in out)
 
             eval_metrics._b200fno_wrapped = True
             _saved["eval_metrics"] = ref_metrics.eval_metrics

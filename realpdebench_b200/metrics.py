@@ -22,7 +22,8 @@ def eval_metrics(pred: torch.Tensor, target: torch.Tensor, c: int, batch_size=No
 
     The tensors may live on the host (``eval.py:342-343`` collects ``pred.cpu()``): each chunk is copied to ``device``
     (default: the tensors' CUDA device, else the current one) right before its C-ABI call, so the concatenated
-    prediction never has to fit in HBM at once."""
+    prediction never has to fit in HBM at once.  ``batch_size=None`` is ONE chunk like the reference (r2 and the
+    spectra depend on the chunking, so it cannot be split behind the caller's back)."""
     if pred.shape != target.shape or pred.dim() != 5:
         raise RuntimeError(f"b200fno: eval_metrics expects two [b,t,h,w,c] tensors, got {tuple(pred.shape)}, {tuple(target.shape)}")
     if device is None:

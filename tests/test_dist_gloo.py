@@ -100,6 +100,10 @@ def _train_worker(rank, world, port, out):
     red = D.GradientAllReducer(m, dist, bucket_bytes=4096)  # small buckets: several messages, some params split off
     red.sync_parameters(0)
     same = all(torch.equal(p.data, sd[k]) for k, p in zip(m.names, m.ps)) and float(m.running.sum()) == 0.0
+    # the broadcast writes through .data (no version bump): the engine's packed-weight key must be invalidated explicitly
+    same = same and getattr(m, "_stats_epoch", 0) == 1
+    red.sync_buffers(0)
+    same = same and m._stats_epoch == 2
     lo, hi = D.shard_range(4, rank, world)
     mine = _grads_of_shard(sd, x[lo:hi], t[lo:hi], s)
     for k, p in zip(m.names, m.ps):

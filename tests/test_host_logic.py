@@ -221,3 +221,25 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, check=True, timeout=120,
                         env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r1.stdout.strip() == ""
+
+
+def test_bench_engine_arm_weights_equal_cpu_arm_weights():
+    """bench.py builds the engine model with the module's own init (no oracle import on the product path); the CPU
+    arm uses oracle.init_state + randomize_bn.  Both must be the same tensors, bit for bit."""
+    import realpdebench_b200 as R
+    import bench
+    for ndim, modes, s in ((2, (3, 4), (2, 12, 14, 3)), (3, (2, 3, 4), (4, 10, 12, 2))):
+        m = bench.build_model(R, ndim, modes, 2, 8, s, s)
+        sd = bench.build_state(ndim, modes, 2, 8, s, s)
+        got = m.state_dict()
+        assert set(got) == set(sd)
+        for k, v in sd.items():
+            assert torch.equal(got[k], v), k
+
+
+def test_bench_loss_check_fixture_matches_bench_workload():
+    import bench
+    ref = bench.oracle_loss_check(bench.DEFAULT_WORKLOAD)
+    ndim, modes, L, width, s_in, s_out, B, n_auto = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    assert ref is not None and ref["batch"] == B and ref["n_autoregressive"] == n_auto and ref["seed"] == 1234
+    assert abs(ref["normalized_loss"] - sum(ref["per_sample"]) / B) < 1e-12
