@@ -221,6 +221,11 @@ int b200fno_eval_metrics(const float* pred, const float* target, int32_t b, int3
 
 /* ---- introspection used by bench.py / tests ------------------------------ */
 /* Kernels launched by this library on this thread since the last reset. */
+/* Diagnostics.  With B200FNO_DEBUG_FINITE set in the environment, b200fno_train_backward scans the output of every
+ * kernel it launches for non-finite values (on the device, in stream order, no host synchronisation).  Returns the id
+ * of the first stage of the last backward that produced one (100 * (layer + 1) + index inside the layer loop; 1..9
+ * projection backward; 9000+ lift backward), 0 if all were finite, < 0 if the facility is off.  Synchronises. */
+int b200fno_debug_first_nonfinite(b200fno_plan_t* plan);
 int64_t b200fno_launch_count(void);
 void b200fno_launch_count_reset(void);
 /* Per-stage device timing: when enabled, every stage launch of forward/rollout is

@@ -20,20 +20,20 @@ bool tc_fwdw_supported(const Geom& g);
 int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, const float* table, long long rows,
                       const Geom& g);
 int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, long long rows, const Geom& g,
-                   cudaStream_t st);
+                   cudaStream_t st, long long row0 = 0);
 bool tc_proj_supported(const Geom& g, int Fout);
 int tc_proj_n2(int Fout);
 int tc_make_proj_act_map(CUtensorMap* m, const float* act, long long rows, const Geom& g, int W);
 int tc_make_fc1_map(CUtensorMap* m, const float* w);
 int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2);
 int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   cudaStream_t st);
+                   cudaStream_t st, int b0 = 0, int nb = -1);
 int tc_lift_nkl(int Fin);
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
-                   cudaStream_t st);
+                   cudaStream_t st, int b0 = 0, int nb = -1);
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
                     const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
-                    cudaStream_t st);
+                    cudaStream_t st, long long row0 = 0);
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -52,6 +52,24 @@ bool& pdl_enabled() { return g_pdl; }
 
 using namespace b200fno;
 
+// Diagnostics (B200FNO_DEBUG_FINITE=1): b200fno_train_backward follows every kernel with a scan of that kernel's output
+// for non-finite values and keeps the smallest stage id that had one (device side, no host synchronisation, so the
+// timing relative to other streams is barely changed).  Stage id = 100 * (layer + 1) + kernel index in the layer loop;
+// 1..9 = projection backward, 9000+ = lift backward.  Read with b200fno_debug_first_nonfinite().
+__global__ void finite_check_kernel(const float* __restrict__ x, size_t n, int stage, int* __restrict__ first) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    bad |= !(fabsf(v) <= 3.0e38f);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicMin(first, stage);
+}
+
+// Activation megabytes per chunk of the chunked launch order (run_network); 0 = whole batch per launch.
+#ifndef B200FNO_L2_CHUNK_MB_DEFAULT
+#define B200FNO_L2_CHUNK_MB_DEFAULT 0.0
+#endif
+
 // Optional per-stage CUDA-event timing (bench.py's roofline numbers are measured with this,
 // on the caller's stream, around the real launches).
 enum Stage { ST_LIFT = 0, ST_FWD_W, ST_FWD_H, ST_FWD_T, ST_MODES, ST_INV_T, ST_INV_H, ST_LAYER, ST_PROJ, ST_COUNT };
@@ -68,8 +86,10 @@ struct StageScope {
   Timing* t;
   cudaStream_t st;
   size_t slot = (size_t)-1;
-  StageScope(Timing* t_, int stage, cudaStream_t s) : t(t_), st(s) {
+  // count = false: a further launch of the same logical stage (batch chunks): its time is added, not its launch
+  StageScope(Timing* t_, int stage, cudaStream_t s, bool count = true) : t(t_), st(s) {
     if (!t || !t->enabled) return;
+    if (!count) stage |= 0x100;
     if (t->used + 2 > t->ev.size()) {
       for (int i = 0; i < 2; ++i) {
         cudaEvent_t e;
@@ -118,7 +138,9 @@ struct b200fno_plan {
   bool weights_ready = false;
   Timing timing;
   // views into ws / packed
-  float *act[2], *bufAD, *bufBC, *bufS, *bufO;
+  float *act[2], *bufA, *bufAD, *bufBC, *bufS, *bufO;  // bufA: forward-W output; bufAD: inverse-H output D
+  int* dbg_first = nullptr;  // B200FNO_DEBUG_FINITE: smallest stage id of b200fno_train_backward with a non-finite output
+  int chunk_b = 0;  // samples per launch of the activation-sized kernels (0: whole batch), see run_network
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
   std::vector<LayerPacked> layers;
   // tensor-core path
@@ -179,6 +201,9 @@ static size_t ad_elems(const Geom& g, int B) {
 static size_t spectral_scratch_floats(const Geom& g, int B) {
   return align_up(ad_elems(g, B), 64) + align_up(g.b_elems(B), 64) + 2 * align_up(g.s_elems(B), 64);
 }
+// the plan keeps A in its own buffer: with the chunked launch order (run_network) the forward-W stage of layer l+1
+// writes A while later chunks of layer l still read D
+static size_t plan_scratch_floats(const Geom& g, int B) { return spectral_scratch_floats(g, B) + align_up(g.a_elems(B), 64); }
 
 // The truncated-DFT spectral operator on a channels-last activation:
 //   act -> D   (everything of SpectralConv3d.forward except the last inverse-W stage,
@@ -186,15 +211,19 @@ static size_t spectral_scratch_floats(const Geom& g, int B) {
 static int run_spectral(const Geom& g, const Tables& tab, int B, const float* act, const float* Wpk, float* bufAD,
                         float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr,
                         bool tc_planes = false, const CUtensorMap* tmFwX = nullptr,
-                        const CUtensorMap* tmFwF = nullptr, const CUtensorMap* tmR4 = nullptr) {
+                        const CUtensorMap* tmFwF = nullptr, const CUtensorMap* tmR4 = nullptr, float* bufA = nullptr,
+                        bool fwdw_done = false) {
   // tmR4: data maps {fwdH, fwdT, invT, invH} when the H/T axis transforms run on the tensor cores
+  // bufA: where A = fwdW(act) lives (default: it shares bufAD with D, which is written after A has been consumed);
+  // fwdw_done: the caller has already launched the forward-W stage into bufA (run_network's chunked order)
+  if (!bufA) bufA = bufAD;
   const long long n_hw = (long long)g.m3 * g.Cp;  // contiguous tail after (h,ri) / (ri,kh)
-  {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
+  if (!fwdw_done) {  // forward W: rows (b,t,h): [K2 x Wp] . [Wp x Cp]
     StageScope sc(tm, ST_FWD_W, st);
     if (tmFwX)
-      B2_TRY(launch_fwdw_tc(*tmFwX, *tmFwF, bufAD, (long long)B * g.Tp * g.Hp, g, st));
+      B2_TRY(launch_fwdw_tc(*tmFwX, *tmFwF, bufA, (long long)B * g.Tp * g.Hp, g, st));
     else
-      B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufAD,
+      B2_TRY(launch_lmul(tab.LF, tab.ldLF, g.K2, g.Wp, act, (long long)g.Wp * g.Cp, g.Cp, bufA,
                          (long long)g.K2 * g.Cp, g.Cp, g.Cp, B * g.Tp * g.Hp, st));
   }
   {  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
@@ -203,7 +232,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
     if (tmR4 && tab.tm_fwdH.ok)
       B2_TRY(launch_tmul_tc(tab.tm_fwdH, tmR4[0], fwdH_out, B * g.Tp, 2LL * g.KH * n_hw, n_hw, 1, 0, 0, st));
     else
-      B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufAD, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
+      B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufA, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
                          2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
   }
   if (g.ndim == 3) {
@@ -411,7 +440,7 @@ int b200fno_plan_get_impl(const b200fno_plan_t* p) {
 size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* p) {
   if (!p) return 0;
   const int B = p->d.max_batch;
-  return (2 * align_up(p->g.act_elems(B), 64) + spectral_scratch_floats(p->g, B)) * sizeof(float);
+  return (2 * align_up(p->g.act_elems(B), 64) + plan_scratch_floats(p->g, B)) * sizeof(float);
 }
 
 static size_t packed_floats(const b200fno_plan* p) {
@@ -450,7 +479,8 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   p->bufAD = w, w += align_up(ad_elems(g, B), 64);
   p->bufBC = w, w += align_up(g.b_elems(B), 64);
   p->bufS = w, w += align_up(g.s_elems(B), 64);
-  p->bufO = w;
+  p->bufO = w, w += align_up(g.s_elems(B), 64);
+  p->bufA = w;
   float* q = (float*)packed;
   p->packed = q, p->packed_bytes = packed_bytes;
   p->W0T = q, q += align_up((size_t)p->Klp * g.Cp, 64);
@@ -505,7 +535,7 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
       const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw, GT = B * g.Tp;
       p->use_tc_tmul = tb.tm_fwdH.ok || tb.tm_invH.ok || tb.tm_fwdT.ok || tb.tm_invT.ok;
       if (tb.tm_fwdH.ok)
-        B2_TRY(tmul_make_data_map(&p->tmR_fwdH, p->bufAD, GT, 2 * g.Hp, n_hw, (long long)g.Hp * 2 * n_hw));
+        B2_TRY(tmul_make_data_map(&p->tmR_fwdH, p->bufA, GT, 2 * g.Hp, n_hw, (long long)g.Hp * 2 * n_hw));
       if (tb.tm_invH.ok)
         B2_TRY(tmul_make_data_map(&p->tmR_invH, g.ndim == 3 ? p->bufBC : p->bufO, GT, 2 * g.KH, n_hw,
                                   2LL * g.KH * n_hw));
@@ -515,6 +545,13 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
         B2_TRY(tmul_make_data_map(&p->tmR_invT, p->bufO, B, 2 * g.KT, n_t, 2LL * g.KT * n_t));
     }
     p->use_tc_fwdw = tc_fwdw_supported(g);
+    {  // samples per launch of the activation-sized kernels (run_network): B200FNO_L2_CHUNK_MB = activation bytes per
+       // chunk that should stay L2-resident between the producing kernel and its consumer (0 disables chunking)
+      const char* e = getenv("B200FNO_L2_CHUNK_MB");
+      const double mb = e ? atof(e) : B200FNO_L2_CHUNK_MB_DEFAULT;
+      const double per_sample = (double)g.Tp * g.Hp * g.Wp * g.Cp * 4 / 1e6;
+      p->chunk_b = mb > 0 ? std::max(1, (int)(mb / per_sample)) : 0;
+    }
     if (p->use_tc_fwdw) {
       B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], p->tab.LF_hl, rows, g));
       B2_TRY(tc_make_fwdw_maps(&p->tmFwX[1], &p->tmFwF, p->act[1], p->tab.LF_hl, rows, g));
@@ -584,22 +621,110 @@ static LiftArgs make_lift_args(const b200fno_plan* p, int B, const float* x, flo
   return la;
 }
 
-// lift + L Fourier layers; leaves the last layer's output in *final_act
-static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final_act, cudaStream_t st) {
+struct ProjSpec {  // what the projection kernel writes (one rollout step or a plain forward)
+  const float *aff_a = nullptr, *aff_b = nullptr;
+  float* out = nullptr;
+  long long out_sB = 0;
+  float* state = nullptr;
+};
+
+static ProjArgs make_proj_args(const b200fno_plan* p, int B, const float* act, const ProjSpec& ps) {
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
-  // the whole trunk is chained with programmatic dependent launches (common.cuh); per-stage event timing sits
+  ProjArgs pa{};
+  pa.act = act, pa.fc1T = p->fc1T, pa.fc1b = p->fc1b, pa.fc2T = p->fc2T, pa.fc2b = p->fc2b;
+  pa.aff_a = ps.aff_a, pa.aff_b = ps.aff_b, pa.chan = p->chan, pa.out_off = p->out_off, pa.st_off = p->st_off;
+  pa.out = ps.out, pa.state = ps.state;
+  pa.B = B, pa.T = p->Tv, pa.H = d.h, pa.W = d.w, pa.Tp = g.Tp, pa.Hp = g.Hp, pa.Wp = g.Wp, pa.Cp = g.Cp;
+  pa.Fout = p->Fout, pa.Fp = p->Fp, pa.c_out = d.c_out, pa.c_in = d.c_in;
+  const long long HW = (long long)d.h * d.w;
+  pa.out_sB = ps.out_sB;
+  pa.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
+  pa.st_sB = (long long)d.t_in * HW * d.c_in;
+  pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
+  return pa;
+}
+
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
+  ~PdlScope() { pdl_enabled() = prev; }
+};
+
+// Projection alone (the training forward uses it after its own trunk): crop -> fc1 -> GELU -> fc2 -> unfold [-> affine]
+static int run_proj(b200fno_plan* p, int B, const float* act, const ProjSpec& ps, cudaStream_t st, bool allow_tc = true) {
+  const ProjArgs pa = make_proj_args(p, B, act, ps);
+  StageScope sc(&p->timing, ST_PROJ, st);
+  PdlScope pdl(p->use_pdl && !p->timing.enabled && allow_tc);  // follows the last layer kernel
+  if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
+  return launch_proj(pa, st);
+}
+
+// FNO3d.forward (fno.py:105-129) = lift, L Fourier layers, projection.
+//
+// Launch order.  Every Fourier layer needs two passes over its input activation - the forward-W transform and the
+// fused layer kernel - and the FFT is global over a sample, so the second pass cannot be fused into the first.  At
+// the headline size an activation (278 MB for 8 samples) is larger than the 126 MB L2, so launched batch-wide the
+// forward-W kernel re-reads from HBM what the previous layer kernel has just written.  On the tensor-core path the
+// activation-sized kernels therefore run per CHUNK of `chunk_b` samples (B200FNO_L2_CHUNK_MB of activation), each
+// producer immediately followed by its consumer on the same chunk:
+//     for c: lift(c), fwdW_0(c)
+//     for l: fwdH, modes, invH on the whole batch;  for c: layer_l(c), then fwdW_{l+1}(c)  (or proj(c) after the last)
+// so the forward-W kernel (and the projection) find their input in L2 and HBM sees the SURVEY 8d traffic: one read
+// and one write of the activation per layer.  The small L2-resident stages stay batch-wide (they are latency bound).
+// A and D live in separate buffers: fwdW_{l+1}(c) writes A while layer_l(c+1) still reads D.
+static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& ps, cudaStream_t st) {
+  const Geom& g = p->g;
+  const b200fno_desc_t& d = p->d;
+  const int L = d.n_layers;
+  // the whole network is chained with programmatic dependent launches (common.cuh); per-stage event timing sits
   // between the launches and would break the chain, so it keeps plain launches.  The lift may overlap the tail of
   // whatever kernel precedes it (projection of the previous rollout step, a weight-pack or a torch kernel): before
   // its pdl_wait() it only touches plan constants.
-  struct PdlScope {
-    bool prev;
-    explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
-    ~PdlScope() { pdl_enabled() = prev; }
-  } pdl_scope(p->use_pdl && !p->timing.enabled);
+  PdlScope pdl_scope(p->use_pdl && !p->timing.enabled);
+  Timing* tm = &p->timing;
+  const long long rows_s = (long long)g.Tp * g.Hp;  // activation rows per sample
+  const CUtensorMap tmR4[4] = {p->tmR_fwdH, p->tmR_fwdT, p->tmR_invT, p->tmR_invH};
   const LiftArgs la = make_lift_args(p, B, x, p->act[0]);
+  const bool all_tc = p->use_tc && p->use_tc_lift && p->use_tc_fwdw && p->use_tc_proj;
+  const int cb = (all_tc && p->chunk_b > 0 && p->chunk_b < B) ? p->chunk_b : B;
+  if (cb < B) {
+    for (int b0 = 0; b0 < B; b0 += cb) {
+      const int nb = std::min(cb, B - b0);
+      {
+        StageScope sc(tm, ST_LIFT, st, b0 == 0);
+        B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st, b0, nb));
+      }
+      StageScope sc(tm, ST_FWD_W, st, b0 == 0);
+      B2_TRY(launch_fwdw_tc(p->tmFwX[0], p->tmFwF, p->bufA, nb * rows_s, g, st, b0 * rows_s));
+    }
+    int cur = 0;
+    for (int l = 0; l < L; ++l) {
+      const LayerPacked& Lp = p->layers[l];
+      B2_TRY(run_spectral(g, p->tab, B, p->act[cur], Lp.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, tm, true,
+                          nullptr, nullptr, p->use_tc_tmul ? tmR4 : nullptr, p->bufA, /*fwdw_done=*/true));
+      for (int b0 = 0; b0 < B; b0 += cb) {
+        const int nb = std::min(cb, B - b0);
+        {
+          StageScope sc(tm, ST_LAYER, st, b0 == 0);
+          B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], Lp.tmW, p->tmD, p->tab.Gt, Lp.scale, Lp.shift,
+                                 nb * rows_s, g, l < L - 1, st, b0 * rows_s));
+        }
+        if (l < L - 1) {
+          StageScope sc(tm, ST_FWD_W, st, b0 == 0);
+          B2_TRY(launch_fwdw_tc(p->tmFwX[cur ^ 1], p->tmFwF, p->bufA, nb * rows_s, g, st, b0 * rows_s));
+        } else {
+          StageScope sc(tm, ST_PROJ, st, b0 == 0);
+          const ProjArgs pa = make_proj_args(p, B, p->act[cur ^ 1], ps);
+          B2_TRY(launch_proj_tc(pa, p->tmActProj[cur ^ 1], p->tmFc1, p->tmFc2, st, b0, nb));
+        }
+      }
+      cur ^= 1;
+    }
+    return 0;
+  }
   {
-    StageScope sc(&p->timing, ST_LIFT, st);
+    StageScope sc(tm, ST_LIFT, st);
     if (p->use_tc_lift) {
       B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st));
     } else {
@@ -607,52 +732,24 @@ static int run_trunk(b200fno_plan* p, int B, const float* x, const float** final
     }
   }
   int cur = 0;
-  const long long rows = (long long)B * g.Tp * g.Hp;
-  const CUtensorMap tmR4[4] = {p->tmR_fwdH, p->tmR_fwdT, p->tmR_invT, p->tmR_invH};
-  for (int l = 0; l < d.n_layers; ++l) {
-    const LayerPacked& L = p->layers[l];
-    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], L.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, &p->timing,
-                        p->use_tc, p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF,
-                        p->use_tc && p->use_tc_tmul ? tmR4 : nullptr));
+  const long long rows = (long long)B * rows_s;
+  for (int l = 0; l < L; ++l) {
+    const LayerPacked& Lp = p->layers[l];
+    B2_TRY(run_spectral(g, p->tab, B, p->act[cur], Lp.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, tm, p->use_tc,
+                        p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF,
+                        p->use_tc && p->use_tc_tmul ? tmR4 : nullptr, p->bufA));
     {
-      StageScope sc(&p->timing, ST_LAYER, st);
+      StageScope sc(tm, ST_LAYER, st);
       if (p->use_tc)
-        B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], L.tmW, p->tmD, p->tab.Gt, L.scale, L.shift, rows, g,
-                               l < d.n_layers - 1, st));
+        B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], Lp.tmW, p->tmD, p->tab.Gt, Lp.scale, Lp.shift, rows, g,
+                               l < L - 1, st));
       else
-        B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], L.convT, p->tab.Gt, p->bufAD, L.scale, L.shift, rows,
-                            g.Wp, g.Cp, g.K2, g.K2p, l < d.n_layers - 1, st));
+        B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], Lp.convT, p->tab.Gt, p->bufAD, Lp.scale, Lp.shift, rows,
+                            g.Wp, g.Cp, g.K2, g.K2p, l < L - 1, st));
     }
     cur ^= 1;
   }
-  *final_act = p->act[cur];
-  return 0;
-}
-
-static int run_proj(b200fno_plan* p, int B, const float* act, const float* aff_a, const float* aff_b, float* out,
-                    long long out_sB, float* state, cudaStream_t st, bool allow_tc = true) {
-  const Geom& g = p->g;
-  const b200fno_desc_t& d = p->d;
-  ProjArgs pa{};
-  pa.act = act, pa.fc1T = p->fc1T, pa.fc1b = p->fc1b, pa.fc2T = p->fc2T, pa.fc2b = p->fc2b;
-  pa.aff_a = aff_a, pa.aff_b = aff_b, pa.chan = p->chan, pa.out_off = p->out_off, pa.st_off = p->st_off;
-  pa.out = out, pa.state = state;
-  pa.B = B, pa.T = p->Tv, pa.H = d.h, pa.W = d.w, pa.Tp = g.Tp, pa.Hp = g.Hp, pa.Wp = g.Wp, pa.Cp = g.Cp;
-  pa.Fout = p->Fout, pa.Fp = p->Fp, pa.c_out = d.c_out, pa.c_in = d.c_in;
-  const long long HW = (long long)d.h * d.w;
-  pa.out_sB = out_sB;
-  pa.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
-  pa.st_sB = (long long)d.t_in * HW * d.c_in;
-  pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
-  StageScope sc(&p->timing, ST_PROJ, st);
-  const bool prev_pdl = pdl_enabled();
-  pdl_enabled() = p->use_pdl && !p->timing.enabled && allow_tc;  // follows the last layer kernel of run_trunk
-  struct Restore {
-    bool v;
-    ~Restore() { pdl_enabled() = v; }
-  } restore{prev_pdl};
-  if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
-  return launch_proj(pa, st);
+  return run_proj(p, B, p->act[cur], ps, st);
 }
 
 static int check_ready(b200fno_plan* p, int batch) {
@@ -678,10 +775,9 @@ int b200fno_forward(b200fno_plan_t* p, int32_t batch, const float* x, float* y, 
     return B200FNO_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const float* fin = nullptr;
-  B2_TRY(run_trunk(p, batch, x, &fin, st));
-  const long long out_sB = (long long)p->d.t_out * p->d.h * p->d.w * p->d.c_out;
-  return run_proj(p, batch, fin, nullptr, nullptr, y, out_sB, nullptr, st);
+  ProjSpec ps;
+  ps.out = y, ps.out_sB = (long long)p->d.t_out * p->d.h * p->d.w * p->d.c_out;
+  return run_network(p, batch, x, ps, st);
 }
 
 int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const float* affine_a, const float* affine_b,
@@ -709,10 +805,10 @@ int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const flo
     B2_TRY(launch_copy_params(x0, state, (long long)batch * d.t_in * HW, d.c_in, d.c_out, st));
   const float* cur = x0;
   for (int i = 0; i < n_steps; ++i) {
-    const float* fin = nullptr;
-    B2_TRY(run_trunk(p, batch, cur, &fin, st));
     float* next = (i + 1 < n_steps) ? state + (size_t)(i & 1) * state_elems : nullptr;
-    B2_TRY(run_proj(p, batch, fin, affine_a, affine_b, pred + (size_t)i * step_elems, out_sB, next, st));
+    ProjSpec ps;
+    ps.aff_a = affine_a, ps.aff_b = affine_b, ps.out = pred + (size_t)i * step_elems, ps.out_sB = out_sB, ps.state = next;
+    B2_TRY(run_network(p, batch, cur, ps, st));
     cur = next;
   }
   return 0;
@@ -794,8 +890,8 @@ int b200fno_timing_collect(b200fno_plan_t* p, double* ms, int64_t* count) {
     B2_CUDA(cudaEventSynchronize(t.ev[s + 1]));
     float f = 0.f;
     B2_CUDA(cudaEventElapsedTime(&f, t.ev[s], t.ev[s + 1]));
-    ms[t.stage[s / 2]] += f;
-    count[t.stage[s / 2]] += 1;
+    ms[t.stage[s / 2] & 0xff] += f;
+    if (!(t.stage[s / 2] & 0x100)) count[t.stage[s / 2] & 0xff] += 1;
   }
   t.used = 0;
   return 0;
@@ -987,7 +1083,9 @@ int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, floa
     B2_TRY(launch_bn_apply(tr.zs[l], tr.xs[l + 1], P, g.Cp, tr.bnc[l], l < L - 1, st));
   }
   const long long out_sB = (long long)d.t_out * d.h * d.w * d.c_out;
-  B2_TRY(run_proj(p, B, tr.xs[L], nullptr, nullptr, y, out_sB, nullptr, st, /*allow_tc=*/false));
+  ProjSpec ps;
+  ps.out = y, ps.out_sB = out_sB;
+  B2_TRY(run_proj(p, B, tr.xs[L], ps, st, /*allow_tc=*/false));
   tr.fwd_done = true, tr.last_batch = B;
   return 0;
 }
@@ -1015,6 +1113,19 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
     if (ptr) B2_CUDA(cudaMemsetAsync(ptr, 0, n * sizeof(float), st));
     return 0;
   };
+  static const bool dbg_on = getenv("B200FNO_DEBUG_FINITE") != nullptr;
+  if (dbg_on) {
+    if (!p->dbg_first) B2_CUDA(cudaMalloc((void**)&p->dbg_first, sizeof(int)));
+    B2_CUDA(cudaMemsetAsync(p->dbg_first, 0x7f, sizeof(int), st));
+  }
+  int dbg_seq = 0;  // checks are numbered in launch order so that the minimum is the first in time
+  auto chk = [&](int stage, const float* ptr, size_t n) -> int {
+    if (dbg_on && ptr) {
+      finite_check_kernel<<<296, 256, 0, st>>>(ptr, n, (++dbg_seq) * 100000 + stage, p->dbg_first);
+      B2_CUDA(cudaGetLastError());
+    }
+    return 0;
+  };
   B2_TRY(zero(gr->fc2_w, (size_t)p->Fout * 128));
   B2_TRY(zero(gr->fc2_b, p->Fout));
   B2_TRY(zero(gr->fc1_w, (size_t)128 * C));
@@ -1034,7 +1145,10 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   const long long HW = (long long)d.h * d.w;
   pb.out_sB = (long long)d.t_out * HW * d.c_out;
   pb.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
+  B2_TRY(chk(1, dy, (size_t)B * pb.out_sB));
   B2_TRY(launch_proj_bwd(pb, st));
+  B2_TRY(chk(2, tr.g0, (size_t)P * Cp));
+  B2_TRY(chk(3, tr.dH, (size_t)P * 128));
   if (gr->fc2_w) B2_TRY(launch_wgrad(tr.dF, p->Fp, p->Fp, p->Fout, tr.G, 128, 128, 128, P, gr->fc2_w, 128, nullptr, st));
   if (gr->fc2_b) B2_TRY(launch_colsum(tr.dF, p->Fp, p->Fout, P, gr->fc2_b, st));
   if (gr->fc1_w) B2_TRY(launch_wgrad(tr.dH, 128, 128, 128, tr.xs[L], Cp, Cp, C, P, gr->fc1_w, C, nullptr, st));
@@ -1050,14 +1164,19 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   for (int l = L - 1; l >= 0; --l) {
     const LayerPacked& Lp = p->layers[l];
     // GELU' (not after the last layer, fno.py:118-119) and BatchNorm backward, in place: gy becomes dz
+    const int sid = 100 * (l + 1);
+    B2_TRY(chk(sid + 0, gy, (size_t)P * Cp));
+    B2_TRY(chk(sid + 1, tr.zs[l], (size_t)P * Cp));
     B2_TRY(launch_bn_backward(gy, tr.zs[l], gy, P, C, Cp, tr.bnc[l], l < L - 1, tr.stats,
                               gr->bn_weight ? gr->bn_weight[l] : nullptr, gr->bn_bias ? gr->bn_bias[l] : nullptr, st));
+    B2_TRY(chk(sid + 2, gy, (size_t)P * Cp));
     if (gr->conv_w && gr->conv_w[l])
       B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.xs[l], Cp, Cp, C, P, gr->conv_w[l], C, nullptr, st));
     if (gr->conv_b && gr->conv_b[l]) B2_TRY(launch_colsum(gy, Cp, C, P, gr->conv_b[l], st));
     // adjoint of irfft_W, ifft_H, ifft_T: the forward kernels with transposed tables
     B2_TRY(launch_lmul(tr.GtT, tab.ldLF, g.K2, g.Wp, gy, (long long)g.Wp * Cp, Cp, p->bufAD, (long long)g.K2 * Cp, Cp, Cp,
                        (int)rows, st));
+    B2_TRY(chk(sid + 3, p->bufAD, g.a_elems(B)));
     float* dO = p->bufO;
     B2_TRY(launch_lmul(tr.LHiT, tab.ldLH, 2 * g.KH, 2 * g.Hp, p->bufAD, (long long)g.Hp * 2 * n_hw, n_hw,
                        g.ndim == 3 ? p->bufBC : dO, 2LL * g.KH * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
@@ -1065,14 +1184,21 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
       B2_TRY(launch_lmul(tr.LTiT, tab.ldLT, 2 * g.KT, 2 * g.Tp, p->bufBC, (long long)g.Tp * 2 * n_t, n_t, dO,
                          2LL * g.KT * n_t, n_t, (int)n_t, B, st));
     // spectral weights: dW = conj(S) (x) dO per mode;  dS = dO (x) conj(W)^T
+    B2_TRY(chk(sid + 4, dO, g.s_elems(B)));
+    B2_TRY(chk(sid + 5, tr.Ssave[l], g.s_elems(B)));
     if (gr->spec_w) {
       B2_TRY(launch_modes_wgrad(tr.Ssave[l], dO, tr.dWpk, B, g.NM, Cp, st));
+      B2_TRY(chk(sid + 6, tr.dWpk, (size_t)g.NM * Cp * 2 * Cp));
       B2_TRY(launch_unpack_spectral_grad(tr.dWpk, gr->spec_w + (size_t)l * p->ncorner, p->ncorner, g, C, C, d.modes1,
                                          d.modes2, tr.slot_t, tr.slot_h, st));
     }
     B2_TRY(ready(l));  // spectral, conv and BatchNorm gradients of layer l
+    B2_TRY(chk(sid + 7, Lp.spec, (size_t)g.NM * Cp * 2 * Cp));
     B2_TRY(launch_pack_spectral_adj(Lp.spec, tr.Wadj, g.NM, Cp, st));
+    B2_TRY(chk(sid + 8, tr.Wadj, (size_t)g.NM * Cp * 2 * Cp));
+    B2_TRY(chk(sid + 9, dO, g.s_elems(B)));
     B2_TRY(launch_modes(dO, tr.Wadj, p->bufS, B, g.NM, Cp, st));
+    B2_TRY(chk(sid + 10, p->bufS, g.s_elems(B)));
     // adjoint of fft_T, fft_H
     const float* dBh = p->bufS;
     if (g.ndim == 3) {
@@ -1083,16 +1209,28 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
     B2_TRY(launch_lmul(tr.LHT, tab.ldLHi, 2 * g.Hp, 2 * g.KH, dBh, 2LL * g.KH * n_hw, n_hw, p->bufAD,
                        (long long)g.Hp * 2 * n_hw, n_hw, (int)n_hw, B * g.Tp, st));
     // dx = dz . conv_w  +  rfft_W^T(dA): the layer kernel with the untransposed conv weight and LF^T
+    B2_TRY(chk(sid + 11, p->bufAD, g.a_elems(B)));
+    B2_TRY(chk(sid + 12, Lp.convW, (size_t)Cp * Cp));
     B2_TRY(launch_layer(gy, other, Lp.convW, tr.LFT, p->bufAD, nullptr, nullptr, rows, g.Wp, Cp, g.K2, g.K2p, 0, st));
+    B2_TRY(chk(sid + 13, other, (size_t)P * Cp));
     std::swap(gy, other);
   }
   // ---- lift backward (fno.py:106-109): d fc0 = dx_0^T . [features | grid | 1]
   if (gr->fc0_w) {
     B2_TRY(launch_lift_features(make_lift_args(p, B, x, nullptr), tr.G, st));
+    B2_TRY(chk(9001, tr.G, (size_t)P * p->Klp));
+    B2_TRY(chk(9002, gy, (size_t)P * Cp));
     // column nf of the feature matrix is the constant 1 at valid points (0 in the pad region): the bias gradient
     B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.G, p->Klp, p->Klp, nf, P, gr->fc0_w, nf, gr->fc0_b, st));
   }
   return 0;
+}
+
+int b200fno_debug_first_nonfinite(b200fno_plan_t* p) {
+  if (!p || !p->dbg_first) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, p->dbg_first, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return v == 0x7f7f7f7f ? 0 : v % 100000;
 }
 
 int b200fno_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

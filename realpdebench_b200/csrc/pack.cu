@@ -149,7 +149,7 @@ int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int 
 __global__ void split_hl_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    float x = src[i], h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    float x = src[i], h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);  // rn, as tc::tf32_hi
     hi[i] = h;
     lo[i] = x - h;
   }

@@ -145,10 +145,11 @@ __global__ void __launch_bounds__(TM * 4) lmul_kernel(const float* __restrict__ 
         float* dst = Og + (long long)(m / mdiv) * strideOm + (long long)(m % mdiv) * strideOmLo + n;
         float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         if (split_off) {  // 3xTF32 operand planes for the tensor-core layer kernel: hi | lo
-          float4 hi = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
-                                  __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
-                                  __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u),
-                                  __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          // hi rounded to nearest tf32 (tc_common.cuh: tf32_hi)
+          float4 hi = make_float4(__uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u),
+                                  __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u),
+                                  __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u),
+                                  __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u));
           *reinterpret_cast<float4*>(dst) = hi;
           *reinterpret_cast<float4*>(dst + split_off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
         } else {
@@ -226,8 +227,10 @@ __global__ void __launch_bounds__(256, 4) modes_kernel(const float* __restrict__
           ldg4(S + (((size_t)(b0 + bb) * 2 + ri) * NM + mode) * Cp + q * 4);
     }
     __syncthreads();
-    const int pair = ty % nbp, sl = ty / nbp;
-    if (sl < nsl) {
+    // work items = (batch pair, i-slice); with few thread groups (Cp >= 128: 256 / 32 = 8) and a full batch pass
+    // (16 pairs) there are more pairs than groups, so every group walks its items
+    for (int item = ty; item < nbp * nsl; item += nty) {
+      const int pair = item % nbp, sl = item / nbp;
       const int bb = pair * 2;
       const bool two = bb + 1 < nb;
       const float* s0 = Ss + (bb * 2) * Cp;

@@ -108,7 +108,7 @@ int build_tables(const Geom& g, int m1, int m2, Tables* t) {
         const float x = host[0][(size_t)k * t->ldLF + w];
         uint32_t u;
         memcpy(&u, &x, 4);
-        u &= 0xFFFFE000u;
+        u = (u + 0x1000u) & 0xFFFFE000u;  // round to nearest tf32 (tc_common.cuh: tf32_hi)
         float hi;
         memcpy(&hi, &u, 4);
         hl[(size_t)k * wpad + w] = hi;

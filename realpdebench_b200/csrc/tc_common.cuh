@@ -260,8 +260,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, i
 // byte offset of 16-byte chunk `c` of row `r` inside a 128B-swizzled tile whose rows are 128 B
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
-// 3xTF32 split: hi keeps the top 19 bits (exactly representable in tf32), lo = x - hi is exact in fp32
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// 3xTF32 split: hi = x ROUNDED TO NEAREST onto the 19 bits tf32 keeps (so the MMA's own truncation of the operand is a
+// no-op), lo = x - hi exact in fp32 and signed, |lo| <= 2^-11 |x|.  With a truncated hi (what the MMA would make of the raw
+// fp32 value) lo is one-signed and twice as large, and the dropped lo*lo term becomes a coherent bias: one spectral
+// convolution then carries 1.0e-6 relative error against 1.4e-7 with the rounded split (plain fp32 FFMA: 4e-7;
+// scripts_tmp/split_study.py).
+__device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t u) { return (u + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(tf32_rn_bits(__float_as_uint(x))); }
 
 // GELU (erf form, the F.gelu default of fno.py:119,124) without branches:
 //   v*Phi(v) = max(v,0) - |v| * 0.5*erfc(|v|/sqrt2),  erfc from Abramowitz-Stegun 7.1.26 (|eps| <= 1.5e-7).
@@ -323,12 +328,12 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
   f2_unpack(f2_fma(f2_pack(-a0, -a1), f2_pack(e0, e1), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
 }
-// 3xTF32 low parts of two values: x - trunc_tf32(x)
-__device__ __forceinline__ void tf32_lo2(uint32_t& r0, uint32_t& r1) {
+// 3xTF32 split of two values: h = rn_tf32(x), r = x - h (in place)
+__device__ __forceinline__ void tf32_split2(uint32_t& r0, uint32_t& r1, uint32_t& h0, uint32_t& h1) {
   const f32x2 x = f2_pack(__uint_as_float(r0), __uint_as_float(r1));
-  const f32x2 hi = f2_pack(__uint_as_float(r0 & 0xFFFFE000u), __uint_as_float(r1 & 0xFFFFE000u));
+  h0 = tf32_rn_bits(r0), h1 = tf32_rn_bits(r1);
   float a, b;
-  f2_unpack(f2_fma(hi, f2_splat(-1.0f), x), a, b);
+  f2_unpack(f2_fma(f2_pack(__uint_as_float(h0), __uint_as_float(h1)), f2_splat(-1.0f), x), a, b);
   r0 = __float_as_uint(a), r1 = __float_as_uint(b);
 }
 

@@ -30,7 +30,7 @@ constexpr int FW_XS = 32768;      // x part of a stage: 2 channel halves x 2 row
 
 struct FwdWArgs {
   float* out;  // [rows][K2][64]
-  int rows, npairs, nchunk, nsub, K2, K2m, ns, stage_bytes;  // K2 output rows; K2m = K2 rounded up to the MMA N step (16)  // ns ring stages of stage_bytes (x chunk + table chunk)
+  int rows, row0, npairs, nchunk, nsub, K2, K2m, ns, stage_bytes;  // K2 output rows; K2m = K2 rounded up to the MMA N step (16)  // ns ring stages of stage_bytes (x chunk + table chunk)
 };
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
         if (elect_one_sync()) {
           uint8_t* st = sX + sx * FW_STAGE;
           mbar_arrive_expect_tx(&x_full[sx], (uint32_t)(FW_XS + 4 * K2 * 128));
-          tma_load_3d(st, &tmX, &x_full[sx], 0, ch * FW_CH, 2 * pair);
-          tma_load_3d(st + 16384, &tmX, &x_full[sx], 32, ch * FW_CH, 2 * pair);
+          tma_load_3d(st, &tmX, &x_full[sx], 0, ch * FW_CH, a.row0 + 2 * pair);
+          tma_load_3d(st + 16384, &tmX, &x_full[sx], 32, ch * FW_CH, a.row0 + 2 * pair);
           for (int hl = 0; hl < 2; ++hl)
             for (int s = 0; s < 2; ++s)
               tma_load_2d(st + FW_XS + (hl * 2 + s) * K2 * 128, &tmF, &x_full[sx], 32 * (2 * ch + s), K2 * hl);
@@ -135,13 +135,14 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(src + (uint32_t)((half * 32 + i) * 128)));
-          tmem_st32(Ahi + half * 32, v);
           if (half == 1) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[sx]);
           }
+          uint32_t hv[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
+          for (int i = 0; i < 32; i += 2) tf32_split2(v[i], v[i + 1], hv[i], hv[i + 1]);
+          tmem_st32(Ahi + half * 32, hv);
           tmem_st32(Alo + half * 32, v);
         }
         tmem_st_wait();
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
       mbar_wait(&acc_full[ab], pab);
       tc_fence_after();
       const int row = 2 * pair + r;
-      float* o = a.out + (size_t)row * K2out * 64 + c;
+      float* o = a.out + (size_t)(a.row0 + row) * K2out * 64 + c;
       for (int c0 = 0; c0 < K2; c0 += 32) {  // 32 accumulator columns (= output rows k) per pass
         uint32_t v[32];
         tmem_ld32(T_ACC + ab * 64 + lane_addr + c0, v);
@@ -206,9 +207,11 @@ int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, cons
 // wrote it front to back, so its tail is still in the 126 MB L2 when this kernel starts; and this kernel
 // leaves the head of the activation in L2 for the layer kernel that reads it next, front to back.
 int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, long long rows, const Geom& g,
-                   cudaStream_t st) {
+                   cudaStream_t st, long long row0) {
+  // rows [row0, row0 + rows) of the activation (a pair whose second row lies beyond the range is loaded - the tensor
+  // map zero-fills past the end of the activation - but only its first row is written)
   FwdWArgs a{};
-  a.out = out, a.rows = (int)rows, a.npairs = (int)((rows + 1) / 2);
+  a.out = out, a.rows = (int)rows, a.row0 = (int)row0, a.npairs = (int)((rows + 1) / 2);
   a.nchunk = ceil_div(g.Wp, FW_CH), a.nsub = tc_fwdw_nsub(g), a.K2 = g.K2, a.K2m = tc_fwdw_k2m(g);
   a.stage_bytes = FW_XS + round_up(512 * a.K2m, 1024);
   a.ns = std::min(FW_NS, (226 * 1024) / a.stage_bytes);

@@ -52,7 +52,7 @@ enum { MODE_LAYER = 0, MODE_LIFT = 1 };
 struct TcLayerArgs {
   const float* Gt;  // [Wp][K2p] inverse-W table (scaled), fp32
   const float *scale, *shift;
-  int rows, Wp, PT, NTW, G, K2p, gelu, nsx;
+  int rows, row0, Wp, PT, NTW, G, K2p, gelu, nsx;  // rows [row0, row0 + rows) of the activation are processed
   // MODE_LIFT only (fno.py:106-111): A tile = [input features | grid coordinates | 1] built from x
   const float* x;
   const int* in_off;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
     }
     __syncwarp();
     for (int it = 0; MODE == MODE_LIFT && a.in_tma && it < n_my; ++it) {
-      const int row = g + it * a.G;
+      const int row = a.row0 + g + it * a.G;
       const int h = row % a.Hp, tt = (row / a.Hp) % a.Tp, b = row / (a.Hp * a.Tp);
       const int sx = it % NSX, px = (it / NSX) & 1;
       mbar_wait(&x_empty[sx], px ^ 1);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
       __syncwarp();
     }
     for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
-      const int row = g + it * a.G;
+      const int row = a.row0 + g + it * a.G;
       const int sx = it % NSX, px = (it / NSX) & 1;
       mbar_wait(&x_empty[sx], px ^ 1);
       if (elect_one_sync()) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
     // ------------------------------------------------------------------ D producer (own warp: the x ring
     // must be able to run its full depth ahead, not be tied to the 2-deep D ring)
     for (int it = 0; MODE == MODE_LAYER && it < n_my; ++it) {
-      const int row = g + it * a.G;
+      const int row = a.row0 + g + it * a.G;
       const int sd = it & 1, pd = (it >> 1) & 1;
       mbar_wait(&d_empty[sd], pd ^ 1);
       if (elect_one_sync()) {
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float x = valid ? __ldg(a.Gt + (size_t)w * K2p + k0 + i) : 0.f;
-          hi[i] = __float_as_uint(x);
-          lo[i] = __float_as_uint(x - tf32_hi(x));
+          const float xh = tf32_hi(x);
+          hi[i] = __float_as_uint(xh);
+          lo[i] = __float_as_uint(x - xh);
         }
         tmem_st8(T_GHI + lane_addr + k0, hi);
         tmem_st8(T_GLO + lane_addr + k0, lo);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
 #pragma unroll
       for (int f = 0; f < NIN; ++f) r[f] = 0u;
       auto gather = [&](int it) {
-        const int row = g + it * a.G;
+        const int row = a.row0 + g + it * a.G;
         const int h = row % a.Hp, tt = (row / a.Hp) % a.Tp, b = row / (a.Hp * a.Tp);
         const int w = PT * j + p;
         const bool valid = p < PT && w < a.W && h < a.H && tt < a.Tv;
@@ -300,8 +301,9 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
           for (int i = 0; i < 8; ++i) {
             const int f = k0 + i;
             const float x = f < NIN ? __uint_as_float(r[f < NIN ? f : 0]) : ex[f >= NIN ? f - NIN : 0];
-            hi[i] = __float_as_uint(x);
-            lo[i] = __float_as_uint(x - tf32_hi(x));
+            const float xh = tf32_hi(x);
+            hi[i] = __float_as_uint(xh);
+            lo[i] = __float_as_uint(x - xh);
           }
           tmem_st8(Ahi + k0, hi);
           tmem_st8(Alo + k0, lo);
@@ -331,14 +333,21 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        tmem_st32(Ahi + half * 32, v);
         if (half == 1) {  // every shared-memory read of this stage has been consumed
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
-        tmem_st32(Alo + half * 32, v);
+        for (int q16 = 0; q16 < 2; ++q16) {  // 16 values at a time: 768 threads leave 80 registers each
+          uint32_t hv[16], lv[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            lv[i] = v[q16 * 16 + i], lv[i + 1] = v[q16 * 16 + i + 1];
+            tf32_split2(lv[i], lv[i + 1], hv[i], hv[i + 1]);
+          }
+          tmem_st16(Ahi + half * 32 + q16 * 16, hv);
+          tmem_st16(Alo + half * 32 + q16 * 16, lv);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int it = grp; it < n_my; it += NGRP) {
       // two groups: group e owns accumulator buffer e and staging buffer e; one group: both alternate per tile
-      const int row = g + it * a.G, t = it & 1, pt = (it >> 1) & 1, buf = it & 1;
+      const int row = a.row0 + g + it * a.G, t = it & 1, pt = (it >> 1) & 1, buf = it & 1;
       mbar_wait(&acc_full[t], pt);
       tc_fence_after();
       uint32_t v[32];
@@ -437,11 +446,11 @@ int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g)
 
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
                     const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
-                    cudaStream_t st) {
+                    cudaStream_t st, long long row0) {
   TcLayerArgs a{};
   tc_layer_tile(g, &a.PT, &a.NTW);
   a.Gt = Gt, a.scale = scale, a.shift = shift;
-  a.rows = (int)rows, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
+  a.rows = (int)rows, a.row0 = (int)row0, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
   a.G = std::max(1, std::min(148 / a.NTW, (int)rows));
   a.nsx = tc_layer_nsx(a.PT, a.K2p);
   B2_CUDA(cudaFuncSetAttribute(tc_layer_kernel<MODE_LAYER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM));
@@ -455,10 +464,12 @@ int tc_lift_nkl(int Fin);
 
 // Lift on tensor cores: act0 = [x | grid | 1] * W0K^T, zero in the pad region.  W0K: [2 (hi|lo)][64 ch][64 k].
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
-                   cudaStream_t st) {
+                   cudaStream_t st, int b0, int nb) {
+  // samples [b0, b0 + nb) of the batch la.B (nb < 0: all of them)
   TcLayerArgs a{};
   tc_layer_tile(g, &a.PT, &a.NTW);
-  a.rows = la.B * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;
+  if (nb < 0) b0 = 0, nb = la.B;
+  a.rows = nb * g.Tp * g.Hp, a.row0 = b0 * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
   a.nsx = tc_layer_nsx(a.PT, 0);  // the lift has no D ring (that area holds its gather tables)
   a.x = la.x, a.in_off = la.in_off, a.gt = la.gt, a.gh = la.gh, a.gw = la.gw;

@@ -34,7 +34,7 @@ struct TcProjArgs {
   const float *aff_a, *aff_b;    // per physical channel or nullptr
   const int *chan, *out_off, *st_off;
   float *out, *state;
-  int rows, Tv, H, W, Tp, Hp, PT, NTW, G, Fout, N2, c_out, c_in;
+  int rows, row0, Tv, H, W, Tp, Hp, PT, NTW, G, Fout, N2, c_out, c_in;  // valid rows [row0, row0 + rows)
   long long out_sB, out_sT, st_sB, st_sT;
   // TMA-store epilogue: the output tile is staged as [box][frame][OB floats] and stored with 4-D boxes over
   // out viewed as [B][frames][H][W*c_out] (and the next-input state when c_in == c_out)
@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       gelu_erf_fast2(y0, y1);
       v[i] = __float_as_uint(y0), v[i + 1] = __float_as_uint(y1);
     }
-    tmem_st16(T_H + lane_addr + col0, v);
+    uint32_t hv[16];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) tf32_lo2(v[i], v[i + 1]);
+    for (int i = 0; i < 16; i += 2) tf32_split2(v[i], v[i + 1], hv[i], hv[i + 1]);
+    tmem_st16(T_H + lane_addr + col0, hv);
     tmem_st16(T_H + 128 + lane_addr + col0, v);
   };
   auto epi1_publish = [&](int chunk) {  // call after tmem_st_wait(): the chunk's hidden quarter may feed GEMM-2
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     }
     __syncwarp();
     for (int it = 0; it < n_my; ++it) {
-      const int prow = padded_row(a.rows - 1 - (g + it * a.G));  // back to front: the tail is still in L2
+      const int prow = padded_row(a.row0 + a.rows - 1 - (g + it * a.G));  // back to front: the tail is still in L2
       const int sx = it % TCP_NSX, px = (it / TCP_NSX) & 1;
       mbar_wait(&x_empty[sx], px ^ 1);
       if (elect_one_sync()) {
@@ -226,13 +227,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        tmem_st32(T_X + lane_addr + half * 32, v);
         if (half == 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
         }
+        uint32_t hv[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
+        for (int i = 0; i < 32; i += 2) tf32_split2(v[i], v[i + 1], hv[i], hv[i + 1]);
+        tmem_st32(T_X + lane_addr + half * 32, hv);
         tmem_st32(T_X + 64 + lane_addr + half * 32, v);
       }
       tmem_st_wait();
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
     }
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ph = it & 1;
-      const int row = a.rows - 1 - (g + it * a.G);
+      const int row = a.row0 + a.rows - 1 - (g + it * a.G);
       const int h = row % a.H, t = (row / a.H) % a.Tv, b = row / (a.H * a.Tv);
       const int w = PT * j + p;
       // ---- epilogue 1: hidden = GELU(acc + b1) -> TMEM as the A operand of GEMM-2 (hi | lo)
@@ -388,11 +390,13 @@ int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2) {  // [2*N2 rows (hl
 }
 
 int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   cudaStream_t st) {
+                   cudaStream_t st, int b0, int nb) {
+  // samples [b0, b0 + nb) of the batch pa.B (nb < 0: all of them)
   TcProjArgs a{};
   a.fc1b = pa.fc1b, a.fc2b = pa.fc2b, a.aff_a = pa.aff_a, a.aff_b = pa.aff_b;
   a.chan = pa.chan, a.out_off = pa.out_off, a.st_off = pa.st_off, a.out = pa.out, a.state = pa.state;
-  a.rows = pa.B * pa.T * pa.H, a.Tv = pa.T, a.H = pa.H, a.W = pa.W, a.Tp = pa.Tp, a.Hp = pa.Hp;
+  if (nb < 0) b0 = 0, nb = pa.B;
+  a.rows = nb * pa.T * pa.H, a.row0 = b0 * pa.T * pa.H, a.Tv = pa.T, a.H = pa.H, a.W = pa.W, a.Tp = pa.Tp, a.Hp = pa.Hp;
   tc_proj_tile(pa.W, &a.PT, &a.NTW);
   a.G = std::max(1, std::min(148 / a.NTW, a.rows));
   a.Fout = pa.Fout, a.N2 = tc_proj_n2(pa.Fout), a.c_out = pa.c_out, a.c_in = pa.c_in;

@@ -145,13 +145,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(src + (uint32_t)((half * 32 + i) * 128)));
-          tmem_st32(Ahi + half * 32, v);
           if (half == 1) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[sx]);
           }
+          uint32_t hv[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) tf32_lo2(v[i], v[i + 1]);
+          for (int i = 0; i < 32; i += 2) tf32_split2(v[i], v[i + 1], hv[i], hv[i + 1]);
+          tmem_st32(Ahi + half * 32, hv);
           tmem_st32(Alo + half * 32, v);
         }
         tmem_st_wait();
@@ -223,7 +224,7 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
       const float x = L[(size_t)m * ldl + k];
       uint32_t u;
       memcpy(&u, &x, 4);
-      u &= 0xFFFFE000u;
+      u = (u + 0x1000u) & 0xFFFFE000u;  // round to nearest tf32 (tc_common.cuh: tf32_hi)
       float hi;
       memcpy(&hi, &u, 4);
       hl[(size_t)m * tp->Kpad + k] = hi;

@@ -298,10 +298,21 @@ class OverlappedGradientReducer:
         grads = engine.train_backward(x, dy, params, ready_events=handles, seq=seq)
         if os.environ.get("B200FNO_REDUCER_SYNC"):  # race probe (profiles/diag_train.py): no overlap at all
             torch.cuda.synchronize(x.device)
+        if os.environ.get("B200FNO_REDUCER_SNAPSHOT"):  # diag: the local gradients as the backward left them
+            self.debug_snapshot = {n: g.clone() for n, g in grads.items()}
         done = torch.cuda.Event()
         done.record(cur)  # fc0 gradients (and everything else) final
         works, total = [], 0
         op = dist.ReduceOp.AVG
+        dbg = os.environ.get("B200FNO_REDUCER_MODE", "")  # diag only: "nonccl" skips the collectives
+
+        class _NoWork:
+            def wait(self):
+                pass
+
+        def all_reduce(t):
+            return _NoWork() if dbg == "nonccl" else dist.all_reduce(t, op=op, async_op=True)
+
         with torch.cuda.stream(self.side):
             for idx in [L] + list(range(L - 1, -1, -1)) + [-1]:
                 self.side.wait_event(self.events[idx] if idx >= 0 else done)
@@ -310,11 +321,22 @@ class OverlappedGradientReducer:
                 for n in names:
                     g = grads[n]
                     if g.numel() >= (1 << 16):  # spectral weights: reduced in place, no flatten copy
-                        works.append((dist.all_reduce(_real_view(g), op=op, async_op=True), None, None))
+                        if dbg == "smallonly":
+                            continue
+                        if dbg == "dummy":  # same NCCL traffic on memory nobody else uses
+                            if not hasattr(self, "_dummy"):
+                                self._dummy = {}
+                            t = self._dummy.setdefault(n, torch.zeros_like(_real_view(g)))
+                            works.append((all_reduce(t), None, None))
+                        elif dbg == "clone":
+                            c = _real_view(g).clone()
+                            works.append((all_reduce(c), c, [g]))
+                        else:
+                            works.append((all_reduce(_real_view(g)), None, None))
                         total += _real_view(g).numel() * 4
                 if small:  # biases, BatchNorm affine, 1x1 conv: one coalesced message per group
                     flat = torch.cat([_real_view(g).reshape(-1) for g in small])
-                    works.append((dist.all_reduce(flat, op=op, async_op=True), flat, small))
+                    works.append((all_reduce(flat), flat, small))
                     total += flat.numel() * 4
             for w, flat, small in works:
                 w.wait()  # the side stream waits for NCCL

@@ -73,6 +73,8 @@ class FNOEngine:
                 check(L.b200fno_plan_set_impl(plan, {"simt": _capi.IMPL_SIMT, "tc": _capi.IMPL_TC}[self.impl]))
             wsb, pkb = L.b200fno_plan_workspace_bytes(plan), L.b200fno_plan_packed_bytes(plan)
             self._ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+            if os.environ.get("B200FNO_POISON_WS"):  # debugging aid: every fp32 word of the workspace starts as NaN
+                self._ws.fill_(0xFF)
             if self._packed is None or self._packed.numel() != pkb or self._packed.device != device:
                 self._packed = torch.empty(pkb, dtype=torch.uint8, device=device)
             check(L.b200fno_plan_bind(plan, self._ws.data_ptr(), wsb, self._packed.data_ptr(), pkb))
@@ -169,6 +171,8 @@ class FNOEngine:
         L = _capi.lib()
         nbytes = L.b200fno_train_workspace_bytes(self._plan)
         self._train_ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if os.environ.get("B200FNO_POISON_WS"):
+            self._train_ws.fill_(0xFF)
         with torch.cuda.device(device):
             check(L.b200fno_train_bind(self._plan, self._train_ws.data_ptr(), nbytes))
 

@@ -119,6 +119,7 @@ def test_three_adam_steps_match_reference_golden(R, golden, case):
     (2, (5, 6, 2, 12, (4, 20, 28, 3), (4, 20, 28, 3)), 3),      # FNO-2D
     (2, (12, 16, 2, 64, (4, 40, 70, 3), (4, 40, 70, 3)), 2),    # FNO-2D, width 64 / modes (12,16): >64-point rows
     (2, (9, 8, 1, 32, (2, 11, 9, 2), (3, 11, 9, 2)), 40),       # batch > 32: several batch passes in the mode kernels
+    (2, (4, 5, 2, 128, (2, 9, 10, 2), (2, 9, 10, 2)), 20),      # width 128, batch > 16: more batch pairs than thread groups
 ])
 def test_gradients_match_oracle_autograd(R, ndim, ctor, batch):
     torch.manual_seed(5)
