@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
   tc_fence_after();
   pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
   const uint32_t tmem = tmem_base_s;
-  const uint32_t T_ACC = tmem, T_A = tmem + 128;  // acc: 2 x 64 cols (K2 <= 64 used); A: 2 x (64 hi | 64 lo)
+  // acc: 2 x 64 cols (K2 <= 64 used); A: 2 x (64 hi | 64 lo); low-order accumulators: 2 x 64 cols
+  const uint32_t T_ACC = tmem, T_A = tmem + 128, T_ACCLO = tmem + 384;
 
   if (warp == 0) {
     int sx = 0, px = 0;  // ring stage and its phase, advanced incrementally (NS is a run-time value: no div / mod)
@@ -93,21 +94,26 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
         mbar_wait(&x_full[sx], px);  // table chunk of this stage has landed
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
-        const uint32_t acc = T_ACC + ab * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
+        // Two accumulators per row pair: the hi*hi products and the two low-order cross terms.  The adder of the
+        // tensor core TRUNCATES when it folds a K step into the fp32 accumulator (test_accumulator_rounding_mode),
+        // a bias of ~0.3 ulp of the running sum per MMA; kept apart, the 2 x 8 cross-term MMAs of every chunk work
+        // on a sum 2^-11 the size, so only the hi*hi chain (1/3 of the MMAs) pays it.  The epilogue adds the two.
+        const uint32_t acc = T_ACC + ab * 64, acc_lo = T_ACCLO + ab * 64, Ahi = T_A + t * 128, Alo = Ahi + 64;
         const uint64_t dF_hi = make_smem_desc(smem_u32(sX) + sx * FW_STAGE + FW_XS, 0, 1024);
         const uint64_t dF_lo = dF_hi + 2 * sub;
         const uint64_t o0 = 0;
         if (elect_one_sync()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Alo + ks * 8, dF_hi + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
+            umma_tf32_ts(acc_lo, Alo + ks * 8, dF_hi + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
                          (ch | ks) != 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Ahi + ks * 8, dF_lo + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
+            umma_tf32_ts(acc_lo, Ahi + ks * 8, dF_lo + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Ahi + ks * 8, dF_hi + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
+            umma_tf32_ts(acc, Ahi + ks * 8, dF_hi + o0 + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
+                         (ch | ks) != 0);
           umma_commit(&a_empty[t]);
           umma_commit(&x_empty[sx]);
           if (ch == nchunk - 1) umma_commit(&acc_full[ab]);
@@ -161,17 +167,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
       const int row = 2 * pair + r;
       float* o = a.out + (size_t)(a.row0 + row) * K2out * 64 + c;
       for (int c0 = 0; c0 < K2; c0 += 32) {  // 32 accumulator columns (= output rows k) per pass
-        uint32_t v[32];
+        uint32_t v[32], vl[32];
         tmem_ld32(T_ACC + ab * 64 + lane_addr + c0, v);
+        tmem_ld32(T_ACCLO + ab * 64 + lane_addr + c0, vl);
         tmem_ld_wait();
-        if (c0 + 32 >= K2) {  // last pass: the accumulator buffer is free again
+        if (c0 + 32 >= K2) {  // last pass: the accumulator buffers are free again
           tc_fence_before();
           mbar_arrive(&acc_empty[ab]);
         }
         if (row < a.rows) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (c0 + k < K2out) o[(size_t)(c0 + k) * 64] = __uint_as_float(v[k]);
+            if (c0 + k < K2out) o[(size_t)(c0 + k) * 64] = __uint_as_float(v[k]) + __uint_as_float(vl[k]);
         }
       }
     }

@@ -104,20 +104,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         mbar_wait(&x_full[sx], px);
         mbar_wait(&a_full[t], pt);
         tc_fence_after();
-        const uint32_t acc = T_ACC + ab * 128, Ahi = T_A + t * 128, Alo = Ahi + 64;
+        // m tiles of at most 64 rows keep the low-order cross terms in their own accumulator (columns 64.. of the
+        // slot): the tensor core's adder truncates, see tc_fwdw.cu
+        const uint32_t acc = T_ACC + ab * 128, acc_lo = MT <= 64 ? acc + 64 : acc, Ahi = T_A + t * 128, Alo = Ahi + 64;
         const uint64_t dL_hi = make_smem_desc(smem_u32(smem) + sx * SB + TM_XS, 0, 1024);
         const uint64_t dL_lo = dL_hi + 2 * sub;
         if (elect_one_sync()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Alo + ks * 8, dL_hi + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
+            umma_tf32_ts(acc_lo, Alo + ks * 8, dL_hi + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
                          (ch | ks) != 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Ahi + ks * 8, dL_lo + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
+            umma_tf32_ts(acc_lo, Ahi + ks * 8, dL_lo + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Ahi + ks * 8, dL_hi + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc, 1);
+            umma_tf32_ts(acc, Ahi + ks * 8, dL_hi + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
+                         MT <= 64 ? (ch | ks) != 0 : 1);
           umma_commit(&a_empty[t]);
           umma_commit(&x_empty[sx]);
           if (ch == nchunk - 1) umma_commit(&acc_full[ab]);
@@ -176,6 +179,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       for (int c0 = eh * mh; c0 < min(MT, eh * mh + mh); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(T_ACC + ab * 128 + lane_addr + c0, v);
+        if (MT <= 64) {  // + the low-order accumulator
+          uint32_t vl[32];
+          tmem_ld32(T_ACC + ab * 128 + 64 + lane_addr + c0, vl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
