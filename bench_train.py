@@ -162,7 +162,8 @@ def run_engine(args):
             "e2e": {"value": world * pts / (e2e_ms * 1e-3), "unit": "field-points/s",
                     "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks.summary(), "phases_ms": phases,
-            "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap, "fused_adam": bool(args.fused_adam), "loss": float(loss.detach())}), flush=True)
+            "allreduce_bytes_per_step": nbytes, "allreduce_overlapped": overlap,
+            "reducer_max_ctas": getattr(reducer, "max_ctas", None), "fused_adam": bool(args.fused_adam), "loss": float(loss.detach())}), flush=True)
     # a step that produced a non-finite loss or parameter is not a measurement: fail loudly on every rank
     finite = bool(torch.isfinite(loss.detach())) and all(
         bool(torch.isfinite(torch.view_as_real(p) if p.is_complex() else p).all()) for p in model.parameters())

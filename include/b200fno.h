@@ -40,7 +40,7 @@ extern "C" {
 /* impl selector for b200fno_plan_set_impl */
 #define B200FNO_IMPL_AUTO 0   /* tensor-core path where the shape allows, else SIMT */
 #define B200FNO_IMPL_SIMT 1   /* fp32 FFMA kernels (every shape) */
-#define B200FNO_IMPL_TC 2     /* tcgen05 3xTF32 kernels (width 64/128 only); error otherwise */
+#define B200FNO_IMPL_TC 2     /* tcgen05 3xTF32 kernels (width 64 only); error otherwise */
 
 typedef struct b200fno_plan b200fno_plan_t;
 
@@ -144,7 +144,12 @@ int b200fno_rollout(b200fno_plan_t* plan, int32_t batch, const float* x0, const 
  *   x [batch][ci][t][h][w] -> y [batch][co][t][h][w]       (ndim 3)
  *   x [batch][ci][h][w]    -> y [batch][co][h][w]          (ndim 2)
  * weights: ncorner device pointers, complex64 [ci][co][m1][m2][m3].
- * workspace: b200fno_spectral_workspace_bytes(...) bytes of device scratch. */
+ * workspace: b200fno_spectral_workspace_bytes(...) bytes of device scratch.
+ * The constant DFT tables of a geometry are built on the first call (one allocation + synchronous upload) and cached
+ * per device; every later call of that geometry only enqueues kernels on `stream` (no allocation, no synchronisation,
+ * capturable).  Width 64 runs the forward transforms on the tensor cores.  b200fno_spectral_cache_clear() frees the
+ * cached tables (synchronise the streams that used them first). */
+void b200fno_spectral_cache_clear(void);
 size_t b200fno_spectral_workspace_bytes(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t,
                                         int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3);
 int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t, int32_t h,

@@ -19,7 +19,7 @@ SYMBOLS = (
     "b200fno_plan_set_impl", "b200fno_plan_get_impl", "b200fno_plan_workspace_bytes", "b200fno_plan_packed_bytes",
     "b200fno_plan_bind", "b200fno_pack_weights", "b200fno_forward", "b200fno_rollout",
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
-    "b200fno_debug_first_nonfinite",
+    "b200fno_debug_first_nonfinite", "b200fno_spectral_cache_clear",
     "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
     "b200fno_timing_collect", "b200fno_selftest_umma", "b200fno_selftest_mma_rate",
     "b200fno_train_workspace_bytes", "b200fno_train_bind", "b200fno_train_forward", "b200fno_train_backward",
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
     L.b200fno_spectral_workspace_bytes.argtypes = [i32] * 10
     L.b200fno_spectral_conv.restype = C.c_int
     L.b200fno_spectral_conv.argtypes = [i32] * 10 + [_fpp, vp, vp, vp, sz, vp]
+    L.b200fno_spectral_cache_clear.restype = None
+    L.b200fno_spectral_cache_clear.argtypes = []
     L.b200fno_debug_first_nonfinite.restype = C.c_int
     L.b200fno_debug_first_nonfinite.argtypes = [C.c_void_p]
     L.b200fno_launch_count.restype = i64

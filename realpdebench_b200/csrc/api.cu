@@ -4,7 +4,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <tuple>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -814,6 +818,43 @@ int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const flo
   return 0;
 }
 
+// Process-wide cache of the constant tables of the stand-alone spectral operator, keyed by device and geometry.
+// Entries live until b200fno_spectral_cache_clear() (kernels in flight read them: clear only after synchronising).
+namespace {
+struct SpectralKey {
+  int dev, ndim, T, H, W, Cp, m1, m2, m3;
+  bool operator<(const SpectralKey& o) const {
+    return std::tie(dev, ndim, T, H, W, Cp, m1, m2, m3) < std::tie(o.dev, o.ndim, o.T, o.H, o.W, o.Cp, o.m1, o.m2, o.m3);
+  }
+};
+std::mutex g_spec_mu;
+std::map<SpectralKey, std::unique_ptr<Tables>> g_spec_tables;
+}  // namespace
+
+static int spectral_tables_cached(const Geom& g, int m1, int m2, const Tables** out) {
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  const SpectralKey key{dev, g.ndim, g.Tp, g.Hp, g.Wp, g.Cp, m1, m2, g.m3};
+  std::lock_guard<std::mutex> lock(g_spec_mu);
+  auto it = g_spec_tables.find(key);
+  if (it == g_spec_tables.end()) {
+    std::unique_ptr<Tables> t(new Tables());
+    B2_TRY(build_tables(g, m1, m2, t.get()));
+    it = g_spec_tables.emplace(key, std::move(t)).first;
+  }
+  *out = it->second.get();
+  return 0;
+}
+
+void b200fno_spectral_cache_clear(void) {
+  std::lock_guard<std::mutex> lock(g_spec_mu);
+  for (auto& kv : g_spec_tables) {
+    cudaSetDevice(kv.first.dev);
+    free_tables(kv.second.get());
+  }
+  g_spec_tables.clear();
+}
+
 size_t b200fno_spectral_workspace_bytes(int32_t ndim, int32_t batch, int32_t ci, int32_t co, int32_t t, int32_t h,
                                         int32_t w, int32_t m1, int32_t m2, int32_t m3) {
   Geom g;
@@ -839,10 +880,11 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
     return B200FNO_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // Tables are rebuilt per call: this entry point is the stand-alone operator used for
-  // layer-level parity and by callers outside FNO3d; the model path keeps them in the plan.
-  Tables tab;
-  B2_TRY(build_tables(g, m1, m2, &tab));
+  // The constant tables of a geometry are built once per device and kept (spectral_table_cache): the call enqueues
+  // kernels only - no allocation, no host synchronisation, CUDA-graph capturable after the first call of a geometry.
+  const Tables* tabp = nullptr;
+  B2_TRY(spectral_tables_cached(g, m1, m2, &tabp));
+  const Tables& tab = *tabp;
   float* ws = (float*)workspace;
   float* a0 = ws;
   ws += align_up(g.act_elems(batch), 64);
@@ -857,22 +899,29 @@ int b200fno_spectral_conv(int32_t ndim, int32_t batch, int32_t ci, int32_t co, i
   float* bufO = ws;
   ws += align_up(g.s_elems(batch), 64);
   float* Wpk = ws;
-  const long long S = (long long)g.Tp * g.Hp * g.Wp;
-  int rc = launch_pack_spectral(weights, ndim == 3 ? 4 : 2, Wpk, g, ci, co, m1, m2, tab.d_ft, tab.d_fh, st);
-  if (!rc) rc = launch_nchw_to_cl(x, a0, batch, ci, S, g.Cp, st);
-  if (!rc) rc = run_spectral(g, tab, batch, a0, Wpk, bufAD, bufBC, bufS, bufO, st);
-  if (!rc)
-    rc = launch_layer(a0, a1, nullptr, tab.Gt, bufAD, nullptr, nullptr, (long long)batch * g.Tp * g.Hp, g.Wp, g.Cp,
-                      g.K2, g.K2p, 0, st);
-  if (!rc) rc = launch_cl_to_nchw(a1, y, batch, co, S, g.Cp, st);
-  // the tables must outlive the kernels that read them
-  cudaError_t e = cudaStreamSynchronize(st);
-  free_tables(&tab);
-  if (!rc && e != cudaSuccess) {
-    set_error("spectral_conv: %s", cudaGetErrorString(e));
-    rc = B200FNO_ECUDA;
+  const long long S = (long long)g.Tp * g.Hp * g.Wp, rows = (long long)batch * g.Tp * g.Hp;
+  B2_TRY(launch_pack_spectral(weights, ndim == 3 ? 4 : 2, Wpk, g, ci, co, m1, m2, tab.d_ft, tab.d_fh, st));
+  B2_TRY(launch_nchw_to_cl(x, a0, batch, ci, S, g.Cp, st));
+  // width 64: the forward W / H / T transforms run on the tensor cores (tensor maps are encoded on the host per call -
+  // the buffers are the caller's); D stays a plain fp32 plane because the inverse-W stage below is the FFMA kernel
+  // (the tcgen05 layer kernel always carries the bypass convolution, which SpectralConv alone does not have)
+  CUtensorMap tmFwX, tmFwF, tmR4[4];
+  const bool tc_fw = tc_fwdw_supported(g);
+  bool tc_tm = false;
+  if (tc_fw) B2_TRY(tc_make_fwdw_maps(&tmFwX, &tmFwF, a0, tab.LF_hl, rows, g));
+  if (g.Cp == 64) {
+    const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw;
+    if (tab.tm_fwdH.ok) B2_TRY(tmul_make_data_map(&tmR4[0], bufAD, batch * g.Tp, 2 * g.Hp, n_hw, (long long)g.Hp * 2 * n_hw));
+    if (tab.tm_fwdT.ok) B2_TRY(tmul_make_data_map(&tmR4[1], bufBC, batch, 2 * g.Tp, n_t, (long long)g.Tp * 2 * n_t));
+    if (tab.tm_invT.ok) B2_TRY(tmul_make_data_map(&tmR4[2], bufO, batch, 2 * g.KT, n_t, 2LL * g.KT * n_t));
+    if (tab.tm_invH.ok)
+      B2_TRY(tmul_make_data_map(&tmR4[3], g.ndim == 3 ? bufBC : bufO, batch * g.Tp, 2 * g.KH, n_hw, 2LL * g.KH * n_hw));
+    tc_tm = tab.tm_fwdH.ok || tab.tm_fwdT.ok || tab.tm_invT.ok || tab.tm_invH.ok;
   }
-  return rc;
+  B2_TRY(run_spectral(g, tab, batch, a0, Wpk, bufAD, bufBC, bufS, bufO, st, nullptr, /*tc_planes=*/false,
+                      tc_fw ? &tmFwX : nullptr, &tmFwF, tc_tm ? tmR4 : nullptr));
+  B2_TRY(launch_layer(a0, a1, nullptr, tab.Gt, bufAD, nullptr, nullptr, rows, g.Wp, g.Cp, g.K2, g.K2p, 0, st));
+  return launch_cl_to_nchw(a1, y, batch, co, S, g.Cp, st);
 }
 
 int b200fno_timing_enable(b200fno_plan_t* p, int on) {

@@ -267,6 +267,22 @@ class OverlappedGradientReducer:
         if dev.type != "cuda":
             raise RuntimeError("OverlappedGradientReducer needs the module on a CUDA device (use GradientAllReducer)")
         self.side = torch.cuda.Stream(device=dev)
+        # The reductions share the SMs with the backward pass.  A stock NCCL communicator launches up to 32 CTAs per
+        # collective on NVLink systems, and while such a kernel waits for a slower peer it holds those SMs: measured on
+        # 8 B200 (profiles/r02_train_bench_n8.json) the overlapped step took 19.2 ms against 11.1 ms with the
+        # all-reduce after the backward.  The overlapped collectives therefore run on their OWN communicator capped at
+        # a few CTAs (NVSwitch needs little: 537 MB per step under a 5 ms backward is ~110 GB/s) - B200FNO_REDUCER_MAX_CTAS.
+        self.group = None
+        max_ctas = int(os.environ.get("B200FNO_REDUCER_MAX_CTAS", "8"))
+        if dist is not None and self.world > 1 and max_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = max_ctas
+                opts.config.min_ctas = min(4, max_ctas)
+                self.group = dist.new_group(backend="nccl", pg_options=opts)
+            except Exception:  # an older torch without ncclConfig: fall back to the default communicator
+                self.group = None
+        self.max_ctas = max_ctas if self.group is not None else 0
         self.events = [torch.cuda.Event() for _ in range(self.n_layers + 1)]
         for e in self.events:  # torch creates the underlying cudaEvent_t lazily on the first record
             e.record(torch.cuda.current_stream(dev))
@@ -311,7 +327,7 @@ class OverlappedGradientReducer:
                 pass
 
         def all_reduce(t):
-            return _NoWork() if dbg == "nonccl" else dist.all_reduce(t, op=op, async_op=True)
+            return _NoWork() if dbg == "nonccl" else dist.all_reduce(t, op=op, group=self.group, async_op=True)
 
         with torch.cuda.stream(self.side):
             for idx in [L] + list(range(L - 1, -1, -1)) + [-1]:
