@@ -294,6 +294,8 @@ def run_engine(args):
     model = build_model(R, ndim, modes, L, width, s_in, s_out).to(dev).eval()
     if args.engine_impl != "auto":
         model.set_impl(args.engine_impl)
+    if args.dtype == "bf16":  # NOT the headline (BASELINE config C2 is fp32): the reference-autocast arithmetic
+        model.set_compute("bf16")
     norm = GaussianStats(dev, **synthetic_stats(s_in[-1], s_out[-1]))
     c_in, c_out = s_in[-1], s_out[-1]
     a, b = R.rollout_affine(norm, c_in, c_out, dev)
@@ -393,7 +395,8 @@ def run_engine(args):
     want = oracle_loss_check(wl) if not (args.batch or args.n_auto) else None
     loss_ok = None
     if want is not None:
-        loss_ok = abs(loss_check - want["normalized_loss"]) <= 1e-5 * abs(want["normalized_loss"])
+        # fp32: 1e-5 relative; bf16 compute mode: the north_star's 1e-2
+        loss_ok = abs(loss_check - want["normalized_loss"]) <= (1e-2 if args.dtype == "bf16" else 1e-5) * abs(want["normalized_loss"])
     if not args.e2e_no_d2h:  # the host copy of the prediction is the device result, bit for bit
         dev_pred = R.rollout(model, norm, x_host, tgt_host, n_auto, unmeasured_c=0)[0]
         host_ok = bool(torch.equal(dev_pred.cpu(), p_host))
@@ -409,7 +412,7 @@ def run_engine(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "field-points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(wl, world),
                 "impl": "b200fno", "engine_impl": args.engine_impl, "e2e": e2e, "host_numa_cpulist": numa, "gpu_launches": launches,
                 "clocks": clocks.summary(), "roofline": roofline, "whole_step": whole,
                 "stages_ms_per_rollout": {k: round(v["ms"], 4) for k, v in stages.items()},
@@ -437,6 +440,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override batch per GPU (not the headline config)")
     ap.add_argument("--n-auto", type=int, default=0, help="override rollout length (not the headline config)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="f32 = the headline (3xTF32, 1e-5 parity); bf16 = the reference's torch.autocast(bfloat16) "
+                         "arithmetic on the engine (Linear / Conv operands in bf16, spectral stages fp32; 1e-2 parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-no-d2h", action="store_true",
                     help="round-1 e2e (only the loss scalar returns to the host); default returns the prediction")

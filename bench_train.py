@@ -38,8 +38,8 @@ def config(wl, B, world):
     return {"workload": wl, "operator": f"fno{ndim}d", "modes": list(modes), "width": width, "n_layers": L,
             "shape_in": list(s_in), "shape_out": list(s_out), "batch_per_gpu": B, "global_batch": B * world,
             "optimizer": "torch.optim.Adam(lr=1e-3) as train.py:290", "parallelism":
-            f"batch-sharded x{world}, gradient all-reduce per step overlapped with the backward pass "
-            "(realpdebench_b200.dist.OverlappedGradientReducer)"}
+            f"batch-sharded x{world}, one gradient all-reduce per step (overlapped with the backward pass up to 4 ranks: "
+            "realpdebench_b200.dist.OverlappedGradientReducer; after it at 8: GradientAllReducer)"}
 
 
 def run_reference(args):
@@ -93,7 +93,10 @@ def run_engine(args):
         optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)  # train.py:290
     # N > 1: the all-reduce runs under the backward pass (events recorded by b200fno_train_backward); --no-overlap
     # falls back to one bucketed all-reduce after loss.backward()
-    overlap = dist is not None and not args.no_overlap
+    # default: overlapped up to 4 ranks, after-backward at 8 - measured on 8 B200 (profiles/r02_train_bench_n8*.json):
+    # 11.05 ms plain vs 12.89 ms overlapped on a capped 8-CTA communicator vs 19.2 ms overlapped on the stock one
+    # (the collectives of 8 ranks wait on each other while holding SMs of the backward pass); --overlap forces it
+    overlap = dist is not None and not args.no_overlap and (world <= 4 or args.overlap)
     reducer = D.OverlappedGradientReducer(model, dist) if overlap else D.GradientAllReducer(model, dist)
     reducer.sync_parameters(0)
     torch.manual_seed(1234 + rank)
@@ -186,6 +189,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--fused-adam", action="store_true", help="realpdebench_b200.optim.FusedAdam instead of torch's Adam")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of under it")
+    ap.add_argument("--overlap", action="store_true", help="force the overlapped all-reduce also beyond 4 ranks")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the bounded CPU sample (--impl reference)")
     args = ap.parse_args()
     (run_reference if args.impl == "reference" else run_engine)(args)

@@ -42,6 +42,13 @@ extern "C" {
 #define B200FNO_IMPL_SIMT 1   /* fp32 FFMA kernels (every shape) */
 #define B200FNO_IMPL_TC 2     /* tcgen05 3xTF32 kernels (width 64 only); error otherwise */
 
+/* compute mode for b200fno_plan_set_compute */
+#define B200FNO_COMPUTE_F32 0   /* fp32 semantics (3xTF32 on the tensor cores): 1e-5 parity with the fp32 reference */
+#define B200FNO_COMPUTE_BF16 1  /* torch.autocast(bfloat16) semantics of the reference: the operands of every
+                                 * Linear / Conv (fc0, the 1x1 convolutions, fc1, fc2) are cast to bf16 and multiplied
+                                 * in ONE tensor-core pass with fp32 accumulation; the FFT stages and the per-mode
+                                 * mixing stay fp32, as do BatchNorm and the tensors in HBM.  1e-2 parity. */
+
 typedef struct b200fno_plan b200fno_plan_t;
 
 /*
@@ -106,6 +113,10 @@ int b200fno_plan_destroy(b200fno_plan_t* plan);
 int b200fno_plan_set_impl(b200fno_plan_t* plan, int impl);
 /* Which implementation the layer kernels resolve to (B200FNO_IMPL_SIMT|TC). */
 int b200fno_plan_get_impl(const b200fno_plan_t* plan);
+/* Arithmetic of the Linear / Conv products (B200FNO_COMPUTE_*).  May be changed at any time; a change invalidates the
+ * packed weights (call b200fno_pack_weights again).  The training entry points require B200FNO_COMPUTE_F32. */
+int b200fno_plan_set_compute(b200fno_plan_t* plan, int compute);
+int b200fno_plan_get_compute(const b200fno_plan_t* plan);
 
 /* Bytes the caller must provide (activation ping-pong + spectral scratch). */
 size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* plan);

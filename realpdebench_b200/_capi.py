@@ -12,11 +12,12 @@ from ._build import LIB_PATH
 
 ABI_VERSION = 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+COMPUTE = {"f32": 0, "bf16": 1}  # B200FNO_COMPUTE_*
 
 # every extern "C" symbol declared in include/b200fno.h
 SYMBOLS = (
     "b200fno_last_error", "b200fno_abi_version", "b200fno_plan_create", "b200fno_plan_destroy",
-    "b200fno_plan_set_impl", "b200fno_plan_get_impl", "b200fno_plan_workspace_bytes", "b200fno_plan_packed_bytes",
+    "b200fno_plan_set_impl", "b200fno_plan_get_impl", "b200fno_plan_set_compute", "b200fno_plan_get_compute", "b200fno_plan_workspace_bytes", "b200fno_plan_packed_bytes",
     "b200fno_plan_bind", "b200fno_pack_weights", "b200fno_forward", "b200fno_rollout",
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
     "b200fno_debug_first_nonfinite", "b200fno_spectral_cache_clear",
@@ -74,6 +75,10 @@ def lib() -> C.CDLL:
     L.b200fno_plan_destroy.argtypes = [vp]
     L.b200fno_plan_set_impl.restype = C.c_int
     L.b200fno_plan_set_impl.argtypes = [vp, C.c_int]
+    L.b200fno_plan_set_compute.restype = C.c_int
+    L.b200fno_plan_set_compute.argtypes = [vp, C.c_int]
+    L.b200fno_plan_get_compute.restype = C.c_int
+    L.b200fno_plan_get_compute.argtypes = [vp]
     L.b200fno_plan_get_impl.restype = C.c_int
     L.b200fno_plan_get_impl.argtypes = [vp]
     L.b200fno_plan_workspace_bytes.restype = sz

@@ -31,13 +31,13 @@ int tc_make_proj_act_map(CUtensorMap* m, const float* act, long long rows, const
 int tc_make_fc1_map(CUtensorMap* m, const float* w);
 int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2);
 int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   cudaStream_t st, int b0 = 0, int nb = -1);
+                   cudaStream_t st, int b0 = 0, int nb = -1, int bf16 = 0);
 int tc_lift_nkl(int Fin);
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
-                   cudaStream_t st, int b0 = 0, int nb = -1);
+                   cudaStream_t st, int b0 = 0, int nb = -1, int bf16 = 0);
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
                     const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
-                    cudaStream_t st, long long row0 = 0);
+                    cudaStream_t st, long long row0 = 0, int bf16 = 0);
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -143,6 +143,7 @@ struct b200fno_plan {
   Timing timing;
   // views into ws / packed
   float *act[2], *bufA, *bufAD, *bufBC, *bufS, *bufO;  // bufA: forward-W output; bufAD: inverse-H output D
+  int bf16 = 0;  // compute mode (b200fno_plan_set_compute): 1 = torch.autocast(bfloat16) semantics for Linear / Conv
   int* dbg_first = nullptr;  // B200FNO_DEBUG_FINITE: smallest stage id of b200fno_train_backward with a non-finite output
   int chunk_b = 0;  // samples per launch of the activation-sized kernels (0: whole batch), see run_network
   float *W0T, *fc1T, *fc1b, *fc2T, *fc2b;
@@ -435,6 +436,16 @@ int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
   p->impl_request = impl;
   return 0;
 }
+int b200fno_plan_set_compute(b200fno_plan_t* p, int compute) {
+  if (!p || (compute != B200FNO_COMPUTE_F32 && compute != B200FNO_COMPUTE_BF16)) {
+    set_error("bad compute selector");
+    return B200FNO_EINVAL;
+  }
+  if (p->bf16 != (compute == B200FNO_COMPUTE_BF16)) p->weights_ready = false;  // the packed copies depend on it
+  p->bf16 = compute == B200FNO_COMPUTE_BF16;
+  return 0;
+}
+int b200fno_plan_get_compute(const b200fno_plan_t* p) { return p ? (p->bf16 ? B200FNO_COMPUTE_BF16 : B200FNO_COMPUTE_F32) : B200FNO_EINVAL; }
 int b200fno_plan_get_impl(const b200fno_plan_t* p) {
   if (!p) return B200FNO_EINVAL;
   const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp;
@@ -580,13 +591,14 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   B2_TRY(launch_pad_copy(w->fc0_b, C, p->W0T + (size_t)nf * g.Cp, g.Cp, st));
   if (p->use_tc_lift) {  // K-major lift weights, then split in place into hi | lo
     B2_TRY(launch_pack_w0k(w->fc0_w, w->fc0_b, C, p->Fin, p->ng, tc_lift_nkl(p->Fin), p->W0K, st));
-    B2_TRY(launch_split_hl(p->W0K, 4096, p->W0K, p->W0K + 4096, st));
+    B2_TRY(launch_split_hl(p->W0K, 4096, p->W0K, p->W0K + 4096, st, p->bf16));
   }
   for (int l = 0; l < p->d.n_layers; ++l) {
     LayerPacked& L = p->layers[l];
     B2_TRY(launch_transpose_pad(w->conv_w[l], C, C, L.convT, g.Cp, g.Cp, st));
     if (g.Cp == C)  // tensor-core operand planes (K-major = the reference [o][i] layout)
-      B2_TRY(launch_split_hl(w->conv_w[l], C * C, L.convHL, L.convHL + align_up((size_t)g.Cp * g.Cp, 64), st));
+      B2_TRY(launch_split_hl(w->conv_w[l], C * C, L.convHL, L.convHL + align_up((size_t)g.Cp * g.Cp, 64), st, p->bf16));
+    if (p->bf16) B2_TRY(launch_round_bf16(L.convT, (size_t)g.Cp * g.Cp, st));
     B2_TRY(launch_fold_bn(w->conv_b[l], w->bn_weight[l], w->bn_bias[l], w->bn_mean[l], w->bn_var[l], p->d.bn_eps, C,
                           g.Cp, L.scale, L.shift, st));
     B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, L.spec, g, C, C, p->d.modes1,
@@ -604,9 +616,14 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
   B2_TRY(launch_pad_copy(w->fc2_b, p->Fout, p->fc2b, p->Fp, st));
   if (p->use_tc_proj) {  // K-major (= reference [out][in]) hi | lo planes for the tensor-core projection
     const int N2 = tc_proj_n2(p->Fout);
-    B2_TRY(launch_split_hl(w->fc1_w, 128 * 64, p->fc1HL, p->fc1HL + 128 * 64, st));
+    B2_TRY(launch_split_hl(w->fc1_w, 128 * 64, p->fc1HL, p->fc1HL + 128 * 64, st, p->bf16));
     B2_TRY(launch_pad_copy(w->fc2_w, p->Fout * 128, p->fc2HL, N2 * 128, st));
-    B2_TRY(launch_split_hl(p->fc2HL, N2 * 128, p->fc2HL, p->fc2HL + N2 * 128, st));
+    B2_TRY(launch_split_hl(p->fc2HL, N2 * 128, p->fc2HL, p->fc2HL + N2 * 128, st, p->bf16));
+  }
+  if (p->bf16) {  // FFMA-path copies of the Linear weights (bias row of W0T included: autocast casts the bias too)
+    B2_TRY(launch_round_bf16(p->W0T, (size_t)p->Klp * g.Cp, st));
+    B2_TRY(launch_round_bf16(p->fc1T, (size_t)g.Cp * 128, st));
+    B2_TRY(launch_round_bf16(p->fc2T, (size_t)128 * p->Fp, st));
   }
   p->weights_ready = true;
   return 0;
@@ -622,6 +639,7 @@ static LiftArgs make_lift_args(const b200fno_plan* p, int B, const float* x, flo
   la.c_in = d.c_in, la.Fin = p->Fin, la.ng = p->ng, la.Klp = p->Klp;
   la.x_sB = (long long)d.t_in * d.h * d.w * d.c_in;
   la.x_sT = d.ndim == 3 ? (long long)d.h * d.w * d.c_in : 0;
+  la.bf16 = p->bf16;
   return la;
 }
 
@@ -646,6 +664,7 @@ static ProjArgs make_proj_args(const b200fno_plan* p, int B, const float* act, c
   pa.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
   pa.st_sB = (long long)d.t_in * HW * d.c_in;
   pa.st_sT = d.ndim == 3 ? HW * d.c_in : 0;
+  pa.bf16 = p->bf16;
   return pa;
 }
 
@@ -660,7 +679,7 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const ProjSpec& ps
   const ProjArgs pa = make_proj_args(p, B, act, ps);
   StageScope sc(&p->timing, ST_PROJ, st);
   PdlScope pdl(p->use_pdl && !p->timing.enabled && allow_tc);  // follows the last layer kernel
-  if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st);
+  if (p->use_tc_proj && allow_tc) return launch_proj_tc(pa, p->tmActProj[act == p->act[0] ? 0 : 1], p->tmFc1, p->tmFc2, st, 0, -1, p->bf16);
   return launch_proj(pa, st);
 }
 
@@ -697,7 +716,7 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
       const int nb = std::min(cb, B - b0);
       {
         StageScope sc(tm, ST_LIFT, st, b0 == 0);
-        B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st, b0, nb));
+        B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st, b0, nb, p->bf16));
       }
       StageScope sc(tm, ST_FWD_W, st, b0 == 0);
       B2_TRY(launch_fwdw_tc(p->tmFwX[0], p->tmFwF, p->bufA, nb * rows_s, g, st, b0 * rows_s));
@@ -712,7 +731,7 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
         {
           StageScope sc(tm, ST_LAYER, st, b0 == 0);
           B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], Lp.tmW, p->tmD, p->tab.Gt, Lp.scale, Lp.shift,
-                                 nb * rows_s, g, l < L - 1, st, b0 * rows_s));
+                                 nb * rows_s, g, l < L - 1, st, b0 * rows_s, p->bf16));
         }
         if (l < L - 1) {
           StageScope sc(tm, ST_FWD_W, st, b0 == 0);
@@ -720,7 +739,7 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
         } else {
           StageScope sc(tm, ST_PROJ, st, b0 == 0);
           const ProjArgs pa = make_proj_args(p, B, p->act[cur ^ 1], ps);
-          B2_TRY(launch_proj_tc(pa, p->tmActProj[cur ^ 1], p->tmFc1, p->tmFc2, st, b0, nb));
+          B2_TRY(launch_proj_tc(pa, p->tmActProj[cur ^ 1], p->tmFc1, p->tmFc2, st, b0, nb, p->bf16));
         }
       }
       cur ^= 1;
@@ -730,7 +749,7 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
   {
     StageScope sc(tm, ST_LIFT, st);
     if (p->use_tc_lift) {
-      B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st));
+      B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, g, st, 0, -1, p->bf16));
     } else {
       B2_TRY(launch_lift(la, st));
     }
@@ -746,10 +765,10 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
       StageScope sc(tm, ST_LAYER, st);
       if (p->use_tc)
         B2_TRY(launch_layer_tc(p->tmAct[cur], p->tmAct[cur ^ 1], Lp.tmW, p->tmD, p->tab.Gt, Lp.scale, Lp.shift, rows, g,
-                               l < L - 1, st));
+                               l < L - 1, st, 0, p->bf16));
       else
         B2_TRY(launch_layer(p->act[cur], p->act[cur ^ 1], Lp.convT, p->tab.Gt, p->bufAD, Lp.scale, Lp.shift, rows,
-                            g.Wp, g.Cp, g.K2, g.K2p, l < L - 1, st));
+                            g.Wp, g.Cp, g.K2, g.K2p, l < L - 1, st, p->bf16));
     }
     cur ^= 1;
   }
@@ -1109,6 +1128,10 @@ int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, floa
   }
   if (!p->tr.bound) {
     set_error("b200fno_train_bind must be called before b200fno_train_forward");
+    return B200FNO_ESTATE;
+  }
+  if (p->bf16) {
+    set_error("the training path computes in fp32 only (B200FNO_COMPUTE_BF16 covers the evaluation forward / rollout)");
     return B200FNO_ESTATE;
   }
   cudaStream_t st = (cudaStream_t)stream;

@@ -132,7 +132,7 @@ int launch_modes(const float* S, const float* Wpk, float* O, int B, int NM, int 
 // out[row][w][o] = f( (sum_i in[row][w][i] convT[i][o] + sum_k Gt[w][k] D[row][k][o]) * scale[o] + shift[o] )
 int launch_layer(const float* act_in, float* act_out, const float* convT, const float* Gt, const float* D,
                  const float* scale, const float* shift, long long rows, int Wp, int Cp, int K2, int K2p, int gelu,
-                 cudaStream_t st);
+                 cudaStream_t st, int bf16 = 0);
 
 struct LiftArgs {
   const float* x;       // [B][T][H][W][c_in]
@@ -142,6 +142,7 @@ struct LiftArgs {
   const float *gt, *gh, *gw;  // grid coordinate tables (gt == nullptr for ndim 2)
   int B, T, H, W, Tp, Hp, Wp, Cp, c_in, Fin, ng, Klp;
   long long x_sB, x_sT;  // element strides of x for batch and (3-D) frame
+  int bf16 = 0;          // bf16 compute mode: features rounded to bf16 (weights rounded when packed)
 };
 int launch_lift(const LiftArgs& a, cudaStream_t st);
 
@@ -154,6 +155,7 @@ struct ProjArgs {
   float* state;                            // next model input or nullptr
   int B, T, H, W, Tp, Hp, Wp, Cp, Fout, Fp, c_out, c_in;
   long long out_sB, out_sT, st_sB, st_sT;
+  int bf16 = 0;  // bf16 compute mode: x and the hidden activations rounded to bf16
 };
 int launch_proj(const ProjArgs& a, cudaStream_t st);
 
@@ -172,7 +174,8 @@ int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, co
 int launch_pad_copy(const float* src, int n, float* dst, int np, cudaStream_t st);
 int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int ng, int nkl, float* out,
                     cudaStream_t st);
-int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st);  // 3xTF32 planes
+int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st, int bf16 = 0);  // 3xTF32 planes
+int launch_round_bf16(float* p, size_t n, cudaStream_t st);  // in place: bf16 compute mode weights
 
 // ---- training path (train.cu) ----------------------------------------------------
 // train-mode BatchNorm over a flat channels-last tensor [P][Cp]; bnc = [mean|rstd|a|b|s1/n|s2/n] x Cp

@@ -146,17 +146,34 @@ int launch_pack_w0k(const float* fc0_w, const float* fc0_b, int C, int Fin, int 
   return 0;
 }
 
-__global__ void split_hl_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
+__device__ __forceinline__ float round_bf16(float x) {  // nearest-even, as tc::bf16_rn
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+// bf16 != 0 (bf16 compute mode): hi = the weight cast to bf16, lo = 0 (the kernels run a single pass)
+__global__ void split_hl_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo,
+                                int bf16) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    float x = src[i], h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);  // rn, as tc::tf32_hi
+    float x = src[i];
+    float h = bf16 ? round_bf16(x) : __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);  // rn, as tc::tf32_hi
     hi[i] = h;
-    lo[i] = x - h;
+    lo[i] = bf16 ? 0.f : x - h;
   }
 }
-int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st) {
-  split_hl_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, n, dst_hi, dst_lo);
+int launch_split_hl(const float* src, int n, float* dst_hi, float* dst_lo, cudaStream_t st, int bf16) {
+  split_hl_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, n, dst_hi, dst_lo, bf16);
   B2_LAUNCHED("split_hl_kernel");
+  return 0;
+}
+__global__ void round_bf16_kernel(float* __restrict__ p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = round_bf16(p[i]);
+}
+int launch_round_bf16(float* p, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  round_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
+  B2_LAUNCHED("round_bf16_kernel");
   return 0;
 }
 

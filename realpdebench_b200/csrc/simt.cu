@@ -61,6 +61,13 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[4][4], const float* __res
   }
 }
 
+// bf16 compute mode (autocast semantics, tc_common.cuh): operand rounded to nearest-even bf16
+__device__ __forceinline__ float bf16r(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+__device__ __forceinline__ float4 bf16r4(float4 v) { return make_float4(bf16r(v.x), bf16r(v.y), bf16r(v.z), bf16r(v.w)); }
+
 __device__ __forceinline__ float gelu_erf(float v) {  // F.gelu default (fno.py:119,124)
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(256) layer_kernel(const float* __restrict__ in
                                                     const float* __restrict__ convT, const float* __restrict__ Gt,
                                                     const float* __restrict__ D, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int Wp, int Cp, int K2, int K2p,
-                                                    int gelu) {
+                                                    int gelu, int bf16) {
   __shared__ __align__(16) float As[64 * LDA];
   __shared__ __align__(16) float Bs[KC * TN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -319,6 +326,7 @@ __global__ void __launch_bounds__(256) layer_kernel(const float* __restrict__ in
         int idx = tid + i * 256, pp = idx >> 3, kk = (idx & 7) * 4;
         int p = p0 + pp, k = k0 + kk;
         ra[i] = (p < Wp && k < Cp) ? ldg4(in_row + (size_t)p * Cp + k) : zero4();
+        if (bf16) ra[i] = bf16r4(ra[i]);  // conv input cast to bf16 (the weights were rounded when packed)
         int kb = idx >> 4, nn = (idx & 15) * 4;
         int kr = k0 + kb, o = o0 + nn;
         rb[i] = (kr < Cp && o < Cp) ? ldg4(convT + (size_t)kr * Cp + o) : zero4();
@@ -372,9 +380,9 @@ __global__ void __launch_bounds__(256) layer_kernel(const float* __restrict__ in
 
 int launch_layer(const float* act_in, float* act_out, const float* convT, const float* Gt, const float* D,
                  const float* scale, const float* shift, long long rows, int Wp, int Cp, int K2, int K2p, int gelu,
-                 cudaStream_t st) {
+                 cudaStream_t st, int bf16) {
   dim3 grid((unsigned)rows, ceil_div(Wp, 64), ceil_div(Cp, TN));
-  layer_kernel<<<grid, 256, 0, st>>>(act_in, act_out, convT, Gt, D, scale, shift, Wp, Cp, K2, K2p, gelu);
+  layer_kernel<<<grid, 256, 0, st>>>(act_in, act_out, convT, Gt, D, scale, shift, Wp, Cp, K2, K2p, gelu, bf16);
   B2_LAUNCHED("layer_kernel");
   return 0;
 }
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(256) lift_kernel(LiftArgs a) {
             v = gi == 0 ? gtv : (gi == 1 ? ghv : a.gw[w]);
           } else if (j == a.Fin + a.ng) v = 1.f;
         }
-        As[pp * LDA + kk] = v;
+        As[pp * LDA + kk] = a.bf16 ? bf16r(v) : v;
       }
       for (int idx = tid; idx < KC * TN / 4; idx += 256) {
         int kb = idx >> 4, nn = (idx & 15) * 4;
@@ -471,8 +479,9 @@ __global__ void __launch_bounds__(256) proj_kernel(ProjArgs a) {
     for (int i = 0; i < 2; ++i) {
       int idx = tid + i * 256, pp = idx >> 3, kk = (idx & 7) * 4;
       int p = p0 + pp, k = k0 + kk;
-      *reinterpret_cast<float4*>(As + pp * LDA + kk) =
-          (p < a.W && k < a.Cp) ? ldg4(in_row + (size_t)p * a.Cp + k) : zero4();
+      float4 xv = (p < a.W && k < a.Cp) ? ldg4(in_row + (size_t)p * a.Cp + k) : zero4();
+      if (a.bf16) xv = bf16r4(xv);
+      *reinterpret_cast<float4*>(As + pp * LDA + kk) = xv;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -490,12 +499,13 @@ __global__ void __launch_bounds__(256) proj_kernel(ProjArgs a) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       float* hrow = Hs + (ty * 4 + r) * LDH;
-      *reinterpret_cast<float4*>(hrow + tx * 4) =
-          make_float4(gelu_erf(acc0[r][0] + b0.x), gelu_erf(acc0[r][1] + b0.y), gelu_erf(acc0[r][2] + b0.z),
-                      gelu_erf(acc0[r][3] + b0.w));
-      *reinterpret_cast<float4*>(hrow + 64 + tx * 4) =
-          make_float4(gelu_erf(acc1[r][0] + b1.x), gelu_erf(acc1[r][1] + b1.y), gelu_erf(acc1[r][2] + b1.z),
-                      gelu_erf(acc1[r][3] + b1.w));
+      float4 h0 = make_float4(gelu_erf(acc0[r][0] + b0.x), gelu_erf(acc0[r][1] + b0.y), gelu_erf(acc0[r][2] + b0.z),
+                              gelu_erf(acc0[r][3] + b0.w));
+      float4 h1 = make_float4(gelu_erf(acc1[r][0] + b1.x), gelu_erf(acc1[r][1] + b1.y), gelu_erf(acc1[r][2] + b1.z),
+                              gelu_erf(acc1[r][3] + b1.w));
+      if (a.bf16) h0 = bf16r4(h0), h1 = bf16r4(h1);  // the fc2 operand is a bf16 tensor under autocast
+      *reinterpret_cast<float4*>(hrow + tx * 4) = h0;
+      *reinterpret_cast<float4*>(hrow + 64 + tx * 4) = h1;
     }
   }
   __syncthreads();

@@ -328,6 +328,12 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
   f2_unpack(f2_fma(f2_pack(-a0, -a1), f2_pack(e0, e1), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
 }
+// bf16 compute mode (torch.autocast(bfloat16) semantics of the reference: Linear / Conv operands are cast to bf16,
+// products accumulate in fp32): the operand rounded to nearest-even bf16.  A bf16 value is exactly representable in
+// tf32, so ONE kind::tf32 MMA pass on rounded operands gives the bf16 x bf16 -> fp32 products exactly.
+__device__ __forceinline__ uint32_t bf16_rn_bits(uint32_t u) { return (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u; }
+__device__ __forceinline__ float bf16_rn(float x) { return __uint_as_float(bf16_rn_bits(__float_as_uint(x))); }
+
 // 3xTF32 split of two values: h = rn_tf32(x), r = x - h (in place)
 __device__ __forceinline__ void tf32_split2(uint32_t& r0, uint32_t& r1, uint32_t& h0, uint32_t& h1) {
   const f32x2 x = f2_pack(__uint_as_float(r0), __uint_as_float(r1));

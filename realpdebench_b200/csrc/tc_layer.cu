@@ -53,6 +53,7 @@ struct TcLayerArgs {
   const float* Gt;  // [Wp][K2p] inverse-W table (scaled), fp32
   const float *scale, *shift;
   int rows, row0, Wp, PT, NTW, G, K2p, gelu, nsx;  // rows [row0, row0 + rows) of the activation are processed
+  int bf16;  // bf16 compute mode: conv / fc0 operands rounded to bf16, one MMA pass (the inverse-W term stays 3xTF32)
   // MODE_LIFT only (fno.py:106-111): A tile = [input features | grid coordinates | 1] built from x
   const float* x;
   const int* in_off;
@@ -200,21 +201,25 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
 #pragma unroll
           for (int ks = 0; ks < NKL; ++ks) {
               const uint64_t o = (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2);
-              umma_tf32_ts(acc, Alo + ks * 8, dW_hi + o, idesc_w, ks > 0);
-              umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + o, idesc_w, 1);
-              umma_tf32_ts(acc, Ahi + ks * 8, dW_hi + o, idesc_w, 1);
+              if (!a.bf16) {
+                umma_tf32_ts(acc, Alo + ks * 8, dW_hi + o, idesc_w, ks > 0);
+                umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + o, idesc_w, 1);
+              }
+              umma_tf32_ts(acc, Ahi + ks * 8, dW_hi + o, idesc_w, a.bf16 ? ks > 0 : 1);
             }
         } else {
-          // small (lo) terms first, then the hi*hi terms
+          // small (lo) terms first, then the hi*hi terms; bf16 mode: the bypass conv is one pass on rounded operands
+          if (!a.bf16) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_tf32_ts(acc, Alo + ks * 8, dW_hi + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
+          }
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Alo + ks * 8, dW_hi + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, ks > 0);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_tf32_ts(acc, Ahi + ks * 8, dW_lo + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc_w, 1);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            if (ks < nk2) umma_tf32_ts(acc, T_GLO + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, 1);
+            if (ks < nk2) umma_tf32_ts(acc, T_GLO + ks * 8, dD_hi + (uint64_t)(ks * 64), idesc_d, (a.bf16 && ks == 0) ? 0 : 1);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             if (ks < nk2) umma_tf32_ts(acc, T_GHI + ks * 8, dD_lo + (uint64_t)(ks * 64), idesc_d, 1);
@@ -301,12 +306,12 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
           for (int i = 0; i < 8; ++i) {
             const int f = k0 + i;
             const float x = f < NIN ? __uint_as_float(r[f < NIN ? f : 0]) : ex[f >= NIN ? f - NIN : 0];
-            const float xh = tf32_hi(x);
+            const float xh = a.bf16 ? bf16_rn(x) : tf32_hi(x);
             hi[i] = __float_as_uint(xh);
             lo[i] = __float_as_uint(x - xh);
           }
           tmem_st8(Ahi + k0, hi);
-          tmem_st8(Alo + k0, lo);
+          if (!a.bf16) tmem_st8(Alo + k0, lo);
         }
         if (it + NSG < n_my) gather(it + NSG);
         tmem_st_wait();
@@ -336,6 +341,12 @@ __global__ void __launch_bounds__(tcl_threads(MODE), 1)
         if (half == 1) {  // every shared-memory read of this stage has been consumed
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
+        }
+        if (a.bf16) {  // operand of the bypass conv rounded to bf16; no low-order plane
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = bf16_rn_bits(v[i]);
+          tmem_st32(Ahi + half * 32, v);
+          continue;
         }
 #pragma unroll
         for (int q16 = 0; q16 < 2; ++q16) {  // 16 values at a time: 768 threads leave 80 registers each
@@ -446,8 +457,9 @@ int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g)
 
 int launch_layer_tc(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const CUtensorMap& tmD,
                     const float* Gt, const float* scale, const float* shift, long long rows, const Geom& g, int gelu,
-                    cudaStream_t st, long long row0) {
+                    cudaStream_t st, long long row0, int bf16) {
   TcLayerArgs a{};
+  a.bf16 = bf16;
   tc_layer_tile(g, &a.PT, &a.NTW);
   a.Gt = Gt, a.scale = scale, a.shift = shift;
   a.rows = (int)rows, a.row0 = (int)row0, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = gelu;
@@ -464,9 +476,10 @@ int tc_lift_nkl(int Fin);
 
 // Lift on tensor cores: act0 = [x | grid | 1] * W0K^T, zero in the pad region.  W0K: [2 (hi|lo)][64 ch][64 k].
 int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorMap& tmW0, const Geom& g,
-                   cudaStream_t st, int b0, int nb) {
+                   cudaStream_t st, int b0, int nb, int bf16) {
   // samples [b0, b0 + nb) of the batch la.B (nb < 0: all of them)
   TcLayerArgs a{};
+  a.bf16 = bf16;
   tc_layer_tile(g, &a.PT, &a.NTW);
   if (nb < 0) b0 = 0, nb = la.B;
   a.rows = nb * g.Tp * g.Hp, a.row0 = b0 * g.Tp * g.Hp, a.Wp = g.Wp, a.K2p = g.K2p, a.gelu = 0;

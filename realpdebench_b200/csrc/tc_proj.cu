@@ -35,6 +35,7 @@ struct TcProjArgs {
   const int *chan, *out_off, *st_off;
   float *out, *state;
   int rows, row0, Tv, H, W, Tp, Hp, PT, NTW, G, Fout, N2, c_out, c_in;  // valid rows [row0, row0 + rows)
+  int bf16;  // bf16 compute mode: x, hidden activations and weights rounded to bf16, one MMA pass per GEMM
   long long out_sB, out_sT, st_sB, st_sT;
   // TMA-store epilogue: the output tile is staged as [box][frame][OB floats] and stored with 4-D boxes over
   // out viewed as [B][frames][H][W*c_out] (and the next-input state when c_in == c_out)
@@ -120,6 +121,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       gelu_erf_fast2(y0, y1);
       v[i] = __float_as_uint(y0), v[i + 1] = __float_as_uint(y1);
     }
+    if (a.bf16) {  // fc1 output and GELU are bf16 tensors under autocast: the fc2 operand is the rounded value
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = bf16_rn_bits(v[i]);
+      tmem_st16(T_H + lane_addr + col0, v);
+      return;
+    }
     uint32_t hv[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) tf32_split2(v[i], v[i + 1], hv[i], hv[i + 1]);
@@ -169,15 +176,18 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
       mbar_wait(&acc_free, ph ^ 1);
       tc_fence_after();
       if (elect_one_sync()) {
+        if (!a.bf16) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32_ts(T_ACC, T_X + 64 + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32_ts(T_ACC, T_X + ks * 8, d1_lo + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, 1);
+        }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_tf32_ts(T_ACC, T_X + 64 + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_tf32_ts(T_ACC, T_X + ks * 8, d1_lo + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, 1);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_tf32_ts(T_ACC, T_X + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1, 1);
+          umma_tf32_ts(T_ACC, T_X + ks * 8, d1_hi + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2), idesc1,
+                       a.bf16 ? ks > 0 : 1);
         umma_commit(&xa_empty);
         umma_commit(&acc1_full);
       }
@@ -195,9 +205,11 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
 #pragma unroll
           for (int ks = (Q == 1 ? 0 : 4 * Q); ks < 4 * Q + 4; ++ks) {
             const uint64_t o = (uint64_t)(ks >> 2) * sub2 + (uint64_t)((ks & 3) * 2);
-            umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2_hi + o, idesc2, ks > 0);
-            umma_tf32_ts(T_ACC, T_H + ks * 8, d2_lo + o, idesc2, 1);
-            umma_tf32_ts(T_ACC, T_H + ks * 8, d2_hi + o, idesc2, 1);
+            if (!a.bf16) {
+              umma_tf32_ts(T_ACC, T_H + 128 + ks * 8, d2_hi + o, idesc2, ks > 0);
+              umma_tf32_ts(T_ACC, T_H + ks * 8, d2_lo + o, idesc2, 1);
+            }
+            umma_tf32_ts(T_ACC, T_H + ks * 8, d2_hi + o, idesc2, a.bf16 ? ks > 0 : 1);
           }
           if (Q == 3) umma_commit(&acc2_full);
         }
@@ -230,6 +242,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1)
         if (half == 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_empty[sx]);
+        }
+        if (a.bf16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = bf16_rn_bits(v[i]);
+          tmem_st32(T_X + lane_addr + half * 32, v);
+          continue;
         }
         uint32_t hv[32];
 #pragma unroll
@@ -390,9 +408,10 @@ int tc_make_fc2_map(CUtensorMap* m, const float* w, int N2) {  // [2*N2 rows (hl
 }
 
 int launch_proj_tc(const ProjArgs& pa, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   cudaStream_t st, int b0, int nb) {
+                   cudaStream_t st, int b0, int nb, int bf16) {
   // samples [b0, b0 + nb) of the batch pa.B (nb < 0: all of them)
   TcProjArgs a{};
+  a.bf16 = bf16;
   a.fc1b = pa.fc1b, a.fc2b = pa.fc2b, a.aff_a = pa.aff_a, a.aff_b = pa.aff_b;
   a.chan = pa.chan, a.out_off = pa.out_off, a.st_off = pa.st_off, a.out = pa.out, a.state = pa.state;
   if (nb < 0) b0 = 0, nb = pa.B;

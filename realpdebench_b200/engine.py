@@ -35,6 +35,7 @@ class FNOEngine:
         self.shape_out = tuple(int(s) for s in shape_out)
         self.padding, self.bn_eps = int(padding), float(bn_eps)
         self.impl = impl
+        self.compute = "f32"  # "f32" | "bf16" (torch.autocast(bfloat16) semantics), see set_compute
         self._plan: Optional[C.c_void_p] = None
         self._max_batch = 0
         self._device: Optional[torch.device] = None
@@ -71,6 +72,7 @@ class FNOEngine:
             self._plan = plan
             if self.impl != "auto":
                 check(L.b200fno_plan_set_impl(plan, {"simt": _capi.IMPL_SIMT, "tc": _capi.IMPL_TC}[self.impl]))
+            check(L.b200fno_plan_set_compute(plan, _capi.COMPUTE[self.compute]))
             wsb, pkb = L.b200fno_plan_workspace_bytes(plan), L.b200fno_plan_packed_bytes(plan)
             self._ws = torch.empty(wsb, dtype=torch.uint8, device=device)
             if os.environ.get("B200FNO_POISON_WS"):  # debugging aid: every fp32 word of the workspace starts as NaN
@@ -79,6 +81,19 @@ class FNOEngine:
                 self._packed = torch.empty(pkb, dtype=torch.uint8, device=device)
             check(L.b200fno_plan_bind(plan, self._ws.data_ptr(), wsb, self._packed.data_ptr(), pkb))
         self._max_batch, self._device, self._weights_key = batch, device, None
+
+    def set_compute(self, compute: str) -> None:
+        """'f32': fp32 semantics (3xTF32 on the tensor cores).  'bf16': the reference under
+        ``torch.autocast(dtype=torch.bfloat16)`` - Linear / Conv operands cast to bf16, one tensor-core
+        pass with fp32 accumulation; FFT stages, mode mixing, BatchNorm and the stored tensors stay fp32."""
+        if compute not in _capi.COMPUTE:
+            raise ValueError(f"compute must be one of {sorted(_capi.COMPUTE)}, got {compute!r}")
+        if compute == self.compute:
+            return
+        self.compute = compute
+        if self._plan is not None:
+            check(_capi.lib().b200fno_plan_set_compute(self._plan, _capi.COMPUTE[compute]))
+            self._weights_key = None  # the packed copies depend on the mode
 
     # -- weights --------------------------------------------------------------
     def _pack(self, sd: dict, stream: int):

@@ -115,7 +115,23 @@ class _EngineFNO(Model):
 
     def set_impl(self, impl: str):
         """'auto' | 'simt' | 'tc' — which layer kernels the engine uses."""
+        compute = getattr(self, "_compute", "f32")
         self._make_engine(impl)
+        self._engine.set_compute(compute)
+
+    def set_compute(self, compute: str):
+        """'f32' (default) | 'bf16'.  'bf16' = what the reference computes under ``torch.autocast(dtype=bfloat16)``
+        (SURVEY F7): Linear / Conv operands in bf16 with fp32 accumulation, everything spectral in fp32; evaluation
+        forward and rollout only.  Inside a ``torch.autocast("cuda", dtype=torch.bfloat16)`` context the eval-mode
+        forward selects it by itself (and returns a bf16 tensor, as the reference module does)."""
+        self._compute = compute
+        self._engine.set_compute(compute)
+
+    def _resolve_compute(self):
+        """(compute, autocast_active): an active CUDA bf16 autocast context overrides the explicit setting."""
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return "bf16", True
+        return getattr(self, "_compute", "f32"), False
 
     def _engine_state(self):
         sd = {k: v for k, v in self.named_parameters()}
@@ -130,8 +146,14 @@ class _EngineFNO(Model):
 
     def forward(self, x):
         sd, key = self._engine_state()
+        compute, autocast = self._resolve_compute()
         if not self.training:
-            return self._engine.forward(x, sd, key)
+            self._engine.set_compute(compute)
+            y = self._engine.forward(x.float() if autocast else x, sd, key)
+            return y.to(torch.bfloat16) if autocast else y  # fc2 is a Linear: bf16 output under autocast
+        if compute != "f32":
+            raise RuntimeError("b200fno: the training path computes in fp32 only; the bf16 (autocast) mode covers the "
+                               "evaluation forward and the rollout")
         # train mode (train.py:325-329): batch-statistics BatchNorm; differentiable w.r.t. every parameter
         names = [k for k, _ in self.named_parameters()]
         return _TrainForward.apply(self, x, names, *[sd[k] for k in names])
@@ -140,6 +162,7 @@ class _EngineFNO(Model):
         """Fused eval.py:313-321 loop; see realpdebench_b200.rollout for the full per-batch protocol."""
         self._check_eval()
         sd, key = self._engine_state()
+        self._engine.set_compute(self._resolve_compute()[0])
         return self._engine.rollout(x0, affine_a, affine_b, n_steps, sd, key, out=out)
 
     def train_loss(self, input, target):
