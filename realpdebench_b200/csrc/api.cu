@@ -21,6 +21,10 @@ int tc_make_act_map(CUtensorMap* m, const float* act, long long rows, const Geom
 int tc_make_w_map(CUtensorMap* m, const float* w_hl);
 int tc_make_d_map(CUtensorMap* m, const float* d, long long rows, const Geom& g);
 bool tc_fwdw_supported(const Geom& g);
+// tc_modes.cu
+bool tc_modes_supported(const Geom& g, int B);
+int tc_make_modes_map(CUtensorMap* m, const float* Wpk, int NM);
+int launch_modes_tc(const CUtensorMap& tmW, const float* S, float* O, int B, int NM, cudaStream_t st);
 int tc_make_fwdw_maps(CUtensorMap* tmX, CUtensorMap* tmF, const float* act, const float* table, long long rows,
                       const Geom& g);
 int launch_fwdw_tc(const CUtensorMap& tmX, const CUtensorMap& tmF, float* out, long long rows, const Geom& g,
@@ -118,6 +122,7 @@ struct LayerPacked {
   float *cbias, *gamma, *beta, *convW;  // training: conv bias, BN affine (unfolded), conv weight [o][i]
   float* convHL;  // [2][Cp][Cp]: conv weight [o][i] as 3xTF32 hi | lo planes (tensor-core path)
   CUtensorMap tmW;
+  CUtensorMap tmModes;  // packed spectral weights, one mode per box (tc_modes.cu)
 };
 
 struct b200fno_plan {
@@ -143,6 +148,7 @@ struct b200fno_plan {
   Timing timing;
   // views into ws / packed
   float *act[2], *bufA, *bufAD, *bufBC, *bufS, *bufO;  // bufA: forward-W output; bufAD: inverse-H output D
+  bool use_tc_modes = false;  // per-mode mixing on the tensor cores (width 64; per call: batch <= 32)
   int bf16 = 0;  // compute mode (b200fno_plan_set_compute): 1 = torch.autocast(bfloat16) semantics for Linear / Conv
   int* dbg_first = nullptr;  // B200FNO_DEBUG_FINITE: smallest stage id of b200fno_train_backward with a non-finite output
   int chunk_b = 0;  // samples per launch of the activation-sized kernels (0: whole batch), see run_network
@@ -217,7 +223,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
                         float* bufBC, float* bufS, float* bufO, cudaStream_t st, Timing* tm = nullptr,
                         bool tc_planes = false, const CUtensorMap* tmFwX = nullptr,
                         const CUtensorMap* tmFwF = nullptr, const CUtensorMap* tmR4 = nullptr, float* bufA = nullptr,
-                        bool fwdw_done = false) {
+                        bool fwdw_done = false, const CUtensorMap* tmModes = nullptr) {
   // tmR4: data maps {fwdH, fwdT, invT, invH} when the H/T axis transforms run on the tensor cores
   // bufA: where A = fwdW(act) lives (default: it shares bufAD with D, which is written after A has been consumed);
   // fwdw_done: the caller has already launched the forward-W stage into bufA (run_network's chunked order)
@@ -251,7 +257,10 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   }
   {
     StageScope sc(tm, ST_MODES, st);
-    B2_TRY(launch_modes(bufS, Wpk, bufO, B, g.NM, g.Cp, st));
+    if (tmModes && tc_modes_supported(g, B))  // width 64, batch <= 32: the mixing GEMM on the tensor cores
+      B2_TRY(launch_modes_tc(*tmModes, bufS, bufO, B, g.NM, st));
+    else
+      B2_TRY(launch_modes(bufS, Wpk, bufO, B, g.NM, g.Cp, st));
   }
   const float* invH_in = bufO;
   if (g.ndim == 3) {
@@ -542,6 +551,9 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
       B2_TRY(tc_make_fc2_map(&p->tmFc2, p->fc2HL, tc_proj_n2(p->Fout)));
     }
   }
+  p->use_tc_modes = tc64 && getenv("B200FNO_NO_TC_MODES") == nullptr;
+  if (p->use_tc_modes)
+    for (auto& L : p->layers) B2_TRY(tc_make_modes_map(&L.tmModes, L.spec, g.NM));
   if (p->use_tc) {
     B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
@@ -725,7 +737,8 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
     for (int l = 0; l < L; ++l) {
       const LayerPacked& Lp = p->layers[l];
       B2_TRY(run_spectral(g, p->tab, B, p->act[cur], Lp.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, tm, true,
-                          nullptr, nullptr, p->use_tc_tmul ? tmR4 : nullptr, p->bufA, /*fwdw_done=*/true));
+                          nullptr, nullptr, p->use_tc_tmul ? tmR4 : nullptr, p->bufA, /*fwdw_done=*/true,
+                          p->use_tc_modes ? &Lp.tmModes : nullptr));
       for (int b0 = 0; b0 < B; b0 += cb) {
         const int nb = std::min(cb, B - b0);
         {
@@ -760,7 +773,8 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
     const LayerPacked& Lp = p->layers[l];
     B2_TRY(run_spectral(g, p->tab, B, p->act[cur], Lp.spec, p->bufAD, p->bufBC, p->bufS, p->bufO, st, tm, p->use_tc,
                         p->use_tc && p->use_tc_fwdw ? &p->tmFwX[cur] : nullptr, &p->tmFwF,
-                        p->use_tc && p->use_tc_tmul ? tmR4 : nullptr, p->bufA));
+                        p->use_tc && p->use_tc_tmul ? tmR4 : nullptr, p->bufA, false,
+                        p->use_tc_modes ? &Lp.tmModes : nullptr));
     {
       StageScope sc(tm, ST_LAYER, st);
       if (p->use_tc)
@@ -996,7 +1010,7 @@ int b200fno_plan_stage_impl(const b200fno_plan_t* p, int32_t stage) {
     case ST_FWD_W: return p->use_tc && p->use_tc_fwdw;
     case ST_FWD_H: return p->use_tc && p->use_tc_tmul && tb.tm_fwdH.ok;
     case ST_FWD_T: return p->use_tc && p->use_tc_tmul && tb.tm_fwdT.ok;
-    case ST_MODES: return 0;
+    case ST_MODES: return p->use_tc_modes;
     case ST_INV_T: return p->use_tc && p->use_tc_tmul && tb.tm_invT.ok;
     case ST_INV_H: return p->use_tc && p->use_tc_tmul && tb.tm_invH.ok;
     case ST_LAYER: return p->use_tc;

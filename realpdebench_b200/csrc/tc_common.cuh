@@ -35,6 +35,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking phase test (no suspend): for producers that feed a second ring opportunistically
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: far beyond any legitimate wait in these kernels; on expiry the kernel traps
 // (the launch fails, the box stays healthy) instead of hanging the GPU.
 __device__ __forceinline__ uint64_t globaltimer_ns() {

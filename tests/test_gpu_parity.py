@@ -253,7 +253,8 @@ def test_c3_fsi_width128_2d_forward(R):
     assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
 
 
-@pytest.mark.parametrize("width,batch", [(128, 17), (128, 33), (64, 33), (160, 21), (32, 70)])
+@pytest.mark.parametrize("width,batch", [(128, 17), (128, 33), (64, 33), (160, 21), (32, 70),
+                                         (64, 1), (64, 9), (64, 16), (64, 17), (64, 32)])  # width 64, batch <= 32: tc_modes_kernel
 def test_mode_mixing_covers_every_batch_entry(R, width, batch):
     """The per-mode mixing kernel stages up to 32 batch entries per pass and spreads (batch pair, channel slice) work
     items over 256 / min(width/4, 32) thread groups.  Round 1 shipped it with one item per group: at width >= 128
@@ -277,6 +278,7 @@ def test_mode_mixing_covers_every_batch_entry(R, width, batch):
     m = m.to(dev()).eval()
     xin = torch.randn(batch, *s)
     y, yref = m(xin.to(dev())).cpu(), O.fno2d_forward(sd, xin, s)
+    assert m.engine.stage_impls()["modes"] == ("tc" if width == 64 else "simt")
     for b in range(batch):
         assert O.rel_l2(y[b], yref[b]) < TOL, f"batch entry {b}"
 

@@ -71,7 +71,7 @@ def build(R, ndim, modes, L, s_in, s_out, seed, gain=1.0):
 
 def assert_tc_path(m, n_auto):
     si = m.engine.stage_impls()
-    for s in ("lift", "fwdW", "layer", "proj"):
+    for s in ("lift", "fwdW", "modes", "layer", "proj"):
         assert si[s] == "tc", (s, si)
 
 
