@@ -125,10 +125,29 @@ struct LayerPacked {
   CUtensorMap tmModes;  // packed spectral weights, one mode per box (tc_modes.cu)
 };
 
+// modes3 in (32, 64] at width 64: the tensor-core kernels hold at most 32 W modes (TMEM: table rows of the inverse-W
+// term; forward-W accumulator width), so the kept W frequencies are handled as TWO slices [0, m3/2) and [m3/2, m3).
+// Each slice is a complete truncated-DFT pipeline of its own (tables with a frequency offset, its own packed weights);
+// the inverse-W terms add up because the layer kernel runs once per slice:
+//   t   = conv(x)  + invW_0(D_0)                       (no BatchNorm / GELU, written to the other activation buffer)
+//   out = f(I . t  + invW_1(D_1))                      (identity "conv" - exact in 3xTF32 -, then BatchNorm + GELU)
+// i.e. one extra activation pass per layer instead of the FFMA kernels (C5 k = 48 / 64: 6.9 / 9.5 ms -> see profiles).
+struct ModeSlice {
+  int kw0 = 0;
+  Tables tab;
+  std::vector<float*> spec;          // per layer: packed weights of this slice [NMs][Cp][2][Cp] (device, owned)
+  std::vector<CUtensorMap> tmModes;  // per layer
+  CUtensorMap tmFwF;                 // forward-W table of this slice
+};
+
 struct b200fno_plan {
   b200fno_desc_t d;
   Geom g;
   Tables tab;
+  Geom gs;                        // geometry of one mode slice (== g when the plan is not split)
+  std::vector<ModeSlice> slices;  // empty unless split
+  float* ident = nullptr;         // split: [identity hi | zero lo] conv planes, unit scale, zero shift (device, owned)
+  CUtensorMap tmWI;
   int device = 0;
   int impl_request = B200FNO_IMPL_AUTO;
   // derived feature bookkeeping
@@ -148,6 +167,7 @@ struct b200fno_plan {
   Timing timing;
   // views into ws / packed
   float *act[2], *bufA, *bufAD, *bufBC, *bufS, *bufO;  // bufA: forward-W output; bufAD: inverse-H output D
+  bool split = false;         // modes3 in (32, 64]: two mode slices on the tensor-core kernels (struct ModeSlice)
   bool use_tc_modes = false;  // per-mode mixing on the tensor cores (width 64; per call: batch <= 32)
   int bf16 = 0;  // compute mode (b200fno_plan_set_compute): 1 = torch.autocast(bfloat16) semantics for Linear / Conv
   int* dbg_first = nullptr;  // B200FNO_DEBUG_FINITE: smallest stage id of b200fno_train_backward with a non-finite output
@@ -420,6 +440,12 @@ int b200fno_plan_create(const b200fno_desc_t* d, b200fno_plan_t** out) {
 int b200fno_plan_destroy(b200fno_plan_t* p) {
   if (!p) return 0;
   free_tables(&p->tab);
+  for (auto& sl : p->slices) {
+    free_tables(&sl.tab);
+    for (float* q : sl.spec)
+      if (q) cudaFree(q);
+  }
+  if (p->ident) cudaFree(p->ident);
   if (p->tr.tbase) cudaFree(p->tr.tbase);
   if (p->d_grid) cudaFree(p->d_grid);
   if (p->d_int) cudaFree(p->d_int);
@@ -427,14 +453,28 @@ int b200fno_plan_destroy(b200fno_plan_t* p) {
   return 0;
 }
 
+// width 64, modes3 in (32, 64], two equal slices the forward-W kernel supports (2 * slice in {16, 32, 48, 64})
+static bool split_geom(const b200fno_plan* p, Geom* gs) {
+  const Geom& g = p->g;
+  if (g.Cp != 64 || p->d.width != 64 || g.m3 <= 32 || g.m3 > 64 || g.m3 % 16 != 0) return false;
+  Geom s = g;
+  s.m3 = g.m3 / 2, s.K2 = 2 * s.m3, s.K2p = s.K2, s.NM = g.KT * g.KH * s.m3;
+  if (!tc_layer_supported(s) || !tc_fwdw_supported(s)) return false;
+  if (gs) *gs = s;
+  return true;
+}
+static bool plan_can_tc(const b200fno_plan* p) {
+  return (tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp) || split_geom(p, nullptr);
+}
+
 int b200fno_plan_set_impl(b200fno_plan_t* p, int impl) {
   if (!p || impl < B200FNO_IMPL_AUTO || impl > B200FNO_IMPL_TC) {
     set_error("bad impl selector");
     return B200FNO_EINVAL;
   }
-  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp;
+  const bool can_tc = plan_can_tc(p);
   if (impl == B200FNO_IMPL_TC && !can_tc) {
-    set_error("tensor-core layer kernel needs width 64 and modes3 a multiple of 4 up to 32; got width %d, modes3 %d",
+    set_error("tensor-core layer kernel needs width 64 and modes3 a multiple of 4 up to 32 (or 48 / 64, run as two slices); got width %d, modes3 %d",
               p->d.width, p->d.modes3);
     return B200FNO_EINVAL;
   }
@@ -457,8 +497,7 @@ int b200fno_plan_set_compute(b200fno_plan_t* p, int compute) {
 int b200fno_plan_get_compute(const b200fno_plan_t* p) { return p ? (p->bf16 ? B200FNO_COMPUTE_BF16 : B200FNO_COMPUTE_F32) : B200FNO_EINVAL; }
 int b200fno_plan_get_impl(const b200fno_plan_t* p) {
   if (!p) return B200FNO_EINVAL;
-  const bool can_tc = tc_layer_supported(p->g) && p->g.K2 == p->g.K2p && p->d.width == p->g.Cp;
-  return (p->impl_request != B200FNO_IMPL_SIMT && can_tc) ? B200FNO_IMPL_TC : B200FNO_IMPL_SIMT;
+  return (p->impl_request != B200FNO_IMPL_SIMT && plan_can_tc(p)) ? B200FNO_IMPL_TC : B200FNO_IMPL_SIMT;
 }
 
 size_t b200fno_plan_workspace_bytes(const b200fno_plan_t* p) {
@@ -533,6 +572,33 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   p->fc2W = q;
   p->weights_ready = false;
   p->use_tc = p->impl_request != B200FNO_IMPL_SIMT && tc_layer_supported(g) && g.K2 == g.K2p && p->d.width == g.Cp;
+  p->gs = g;
+  const bool split = !p->use_tc && p->impl_request != B200FNO_IMPL_SIMT && split_geom(p, &p->gs) &&
+                     getenv("B200FNO_NO_MODE_SPLIT") == nullptr;
+  if (split && p->slices.empty()) {  // two mode slices (struct ModeSlice): tables, packed-weight buffers, identity planes
+    p->slices.resize(2);
+    const size_t spec_floats = align_up((size_t)p->gs.NM * g.Cp * 2 * g.Cp, 64);
+    for (int s = 0; s < 2; ++s) {
+      ModeSlice& sl = p->slices[s];
+      sl.kw0 = s * p->gs.m3;
+      B2_TRY(build_tables(p->gs, p->d.modes1, p->d.modes2, &sl.tab, sl.kw0));
+      sl.spec.assign(p->d.n_layers, nullptr);
+      sl.tmModes.resize(p->d.n_layers);
+      for (int l = 0; l < p->d.n_layers; ++l) {
+        B2_CUDA(cudaMalloc((void**)&sl.spec[l], spec_floats * sizeof(float)));
+        B2_TRY(tc_make_modes_map(&sl.tmModes[l], sl.spec[l], p->gs.NM));
+      }
+    }
+    std::vector<float> id(2 * 4096 + 128, 0.f);
+    for (int i = 0; i < 64; ++i) id[(size_t)i * 64 + i] = 1.f, id[2 * 4096 + i] = 1.f;  // hi = I, lo = 0; scale = 1; shift = 0
+    B2_CUDA(cudaMalloc((void**)&p->ident, id.size() * sizeof(float)));
+    B2_CUDA(cudaMemcpy(p->ident, id.data(), id.size() * sizeof(float), cudaMemcpyHostToDevice));
+    B2_TRY(tc_make_w_map(&p->tmWI, p->ident));
+  }
+  p->split = split;
+  if (split) p->use_tc = true;
+  const Geom& gt = p->gs;                                      // geometry the tensor-core maps are built for
+  const Tables& tbt = split ? p->slices[0].tab : p->tab;       // (the H / T tables do not depend on the W slice)
   // the lift and the projection do not depend on the mode count: they run on the tensor cores for every width-64
   // model, also where the layer kernel itself has to fall back to the FFMA version (modes3 > 32)
   const bool tc64 = p->impl_request != B200FNO_IMPL_SIMT && g.Cp == 64 && p->d.width == 64;
@@ -555,11 +621,11 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
   if (p->use_tc_modes)
     for (auto& L : p->layers) B2_TRY(tc_make_modes_map(&L.tmModes, L.spec, g.NM));
   if (p->use_tc) {
-    B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, g));
+    B2_TRY(tc_make_d_map(&p->tmD, p->bufAD, rows, gt));
     for (auto& L : p->layers) B2_TRY(tc_make_w_map(&L.tmW, L.convHL));
     {  // H / T axis transforms on the tensor cores
-      const Tables& tb = p->tab;
-      const int n_hw = g.m3 * g.Cp, n_t = g.KH * n_hw, GT = B * g.Tp;
+      const Tables& tb = tbt;
+      const int n_hw = gt.m3 * g.Cp, n_t = g.KH * n_hw, GT = B * g.Tp;
       p->use_tc_tmul = tb.tm_fwdH.ok || tb.tm_invH.ok || tb.tm_fwdT.ok || tb.tm_invT.ok;
       if (tb.tm_fwdH.ok)
         B2_TRY(tmul_make_data_map(&p->tmR_fwdH, p->bufA, GT, 2 * g.Hp, n_hw, (long long)g.Hp * 2 * n_hw));
@@ -571,7 +637,7 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
       if (tb.tm_invT.ok)
         B2_TRY(tmul_make_data_map(&p->tmR_invT, p->bufO, B, 2 * g.KT, n_t, 2LL * g.KT * n_t));
     }
-    p->use_tc_fwdw = tc_fwdw_supported(g);
+    p->use_tc_fwdw = tc_fwdw_supported(gt);
     {  // samples per launch of the activation-sized kernels (run_network): B200FNO_L2_CHUNK_MB = activation bytes per
        // chunk that should stay L2-resident between the producing kernel and its consumer (0 disables chunking)
       const char* e = getenv("B200FNO_L2_CHUNK_MB");
@@ -580,8 +646,10 @@ int b200fno_plan_bind(b200fno_plan_t* p, void* workspace, size_t workspace_bytes
       p->chunk_b = mb > 0 ? std::max(1, (int)(mb / per_sample)) : 0;
     }
     if (p->use_tc_fwdw) {
-      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], p->tab.LF_hl, rows, g));
-      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[1], &p->tmFwF, p->act[1], p->tab.LF_hl, rows, g));
+      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[0], &p->tmFwF, p->act[0], tbt.LF_hl, rows, gt));
+      B2_TRY(tc_make_fwdw_maps(&p->tmFwX[1], &p->tmFwF, p->act[1], tbt.LF_hl, rows, gt));
+      CUtensorMap tmp;
+      for (auto& sl : p->slices) B2_TRY(tc_make_fwdw_maps(&tmp, &sl.tmFwF, p->act[0], sl.tab.LF_hl, rows, gt));
     }
   }
   return 0;
@@ -615,6 +683,9 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
                           g.Cp, L.scale, L.shift, st));
     B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, L.spec, g, C, C, p->d.modes1,
                                 p->d.modes2, p->tab.d_ft, p->tab.d_fh, st));
+    for (auto& sl : p->slices)  // the same weights, W modes [kw0, kw0 + m3 / 2) only (the full pack serves training)
+      B2_TRY(launch_pack_spectral(w->spec_w + (size_t)l * p->ncorner, p->ncorner, sl.spec[l], p->gs, C, C, p->d.modes1,
+                                  p->d.modes2, sl.tab.d_ft, sl.tab.d_fh, st, g.m3, sl.kw0));
     B2_TRY(launch_pad_copy(w->conv_b[l], C, L.cbias, g.Cp, st));
     B2_TRY(launch_pad_copy(w->bn_weight[l], C, L.gamma, g.Cp, st));
     B2_TRY(launch_pad_copy(w->bn_bias[l], C, L.beta, g.Cp, st));
@@ -721,6 +792,37 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
   const long long rows_s = (long long)g.Tp * g.Hp;  // activation rows per sample
   const CUtensorMap tmR4[4] = {p->tmR_fwdH, p->tmR_fwdT, p->tmR_invT, p->tmR_invH};
   const LiftArgs la = make_lift_args(p, B, x, p->act[0]);
+  if (p->split) {  // modes3 in (32, 64]: two mode slices per layer (struct ModeSlice); the layer output returns to
+                   // the buffer its input came from, so `cur` never flips
+    const Geom& gs = p->gs;
+    const long long rows = (long long)B * rows_s;
+    const float *unit = p->ident + 2 * 4096, *zero = unit + 64;
+    {
+      StageScope sc(tm, ST_LIFT, st);
+      if (p->use_tc_lift)
+        B2_TRY(launch_lift_tc(la, p->tmAct[0], p->tmW0, gs, st, 0, -1, p->bf16));
+      else
+        B2_TRY(launch_lift(la, st));
+    }
+    for (int l = 0; l < L; ++l) {
+      const LayerPacked& Lp = p->layers[l];
+      for (int s = 0; s < 2; ++s) {
+        const ModeSlice& sl = p->slices[s];
+        // both slices transform the layer INPUT act[0]; slice 0's layer pass leaves it intact (it writes act[1])
+        B2_TRY(run_spectral(gs, sl.tab, B, p->act[0], sl.spec[l], p->bufAD, p->bufBC, p->bufS, p->bufO, st, tm, true,
+                            &p->tmFwX[0], &sl.tmFwF, p->use_tc_tmul ? tmR4 : nullptr, p->bufA, false,
+                            p->use_tc_modes ? &sl.tmModes[l] : nullptr));
+        StageScope sc(tm, ST_LAYER, st);
+        if (s == 0)
+          B2_TRY(launch_layer_tc(p->tmAct[0], p->tmAct[1], Lp.tmW, p->tmD, sl.tab.Gt, unit, zero, rows, gs, 0, st, 0,
+                                 p->bf16));
+        else  // identity weights: no operand rounding in bf16 mode either (t is a partial sum, not a conv operand)
+          B2_TRY(launch_layer_tc(p->tmAct[1], p->tmAct[0], p->tmWI, p->tmD, sl.tab.Gt, Lp.scale, Lp.shift, rows, gs,
+                                 l < L - 1, st, 0, 0));
+      }
+    }
+    return run_proj(p, B, p->act[0], ps, st);
+  }
   const bool all_tc = p->use_tc && p->use_tc_lift && p->use_tc_fwdw && p->use_tc_proj;
   const int cb = (all_tc && p->chunk_b > 0 && p->chunk_b < B) ? p->chunk_b : B;
   if (cb < B) {
@@ -1004,10 +1106,10 @@ int b200fno_plan_stage_impl(const b200fno_plan_t* p, int32_t stage) {
     set_error("b200fno_plan_stage_impl: bound plan and a stage in [0, %d) required", (int)ST_COUNT);
     return B200FNO_EINVAL;
   }
-  const Tables& tb = p->tab;
+  const Tables& tb = p->split ? p->slices[0].tab : p->tab;
   switch (stage) {
     case ST_LIFT: return p->use_tc_lift;
-    case ST_FWD_W: return p->use_tc && p->use_tc_fwdw;
+    case ST_FWD_W: return p->use_tc && p->use_tc_fwdw;  // (tb below: the H / T plans of slice 0 when the plan is split)
     case ST_FWD_H: return p->use_tc && p->use_tc_tmul && tb.tm_fwdH.ok;
     case ST_FWD_T: return p->use_tc && p->use_tc_tmul && tb.tm_fwdT.ok;
     case ST_MODES: return p->use_tc_modes;

@@ -118,8 +118,8 @@ struct Tables {
   float* LF_hl = nullptr;  // forward-W table as hi|lo planes [2][K2][wpad] (tc_fwdw.cu)
   TmulPlan tm_fwdH, tm_fwdT, tm_invT, tm_invH;  // tensor-core versions of the small axis transforms
 };
-int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6]);
-int build_tables(const Geom& g, int m1, int m2, Tables* t);
+int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6], int kw0 = 0);
+int build_tables(const Geom& g, int m1, int m2, Tables* t, int kw0 = 0);
 void free_tables(Tables* t);
 
 // ---- SIMT stage launchers (simt.cu) ------------------------------------------
@@ -166,7 +166,8 @@ int launch_copy_params(const float* x0, float* state, long long points, int c_in
 
 // ---- weight packing (pack.cu) --------------------------------------------------
 int launch_pack_spectral(const float* const* corners_dev, int ncorner, float* Wpk, const Geom& g, int ci, int co,
-                         int m1, int m2, const int* d_ft, const int* d_fh, cudaStream_t st);
+                         int m1, int m2, const int* d_ft, const int* d_fh, cudaStream_t st, int m3_src = 0, int kw0 = 0);
+// m3_src / kw0: the corner tensors hold m3_src (> g.m3) W modes and this pack takes [kw0, kw0 + g.m3) of them
 int launch_transpose_pad(const float* src, int rows, int cols, float* dst, int dst_rows, int dst_cols,
                          cudaStream_t st);  // dst[c][r] = src[r][c], zero elsewhere
 int launch_fold_bn(const float* conv_b, const float* bn_w, const float* bn_b, const float* bn_m, const float* bn_v,

@@ -21,7 +21,8 @@ struct Corners {
 // transposed through shared memory so that both sides are coalesced (this runs after every optimiser step).
 __global__ void __launch_bounds__(256) pack_spectral_kernel(Corners c, float* __restrict__ Wpk, int ndim, int Tp, int Hp,
                                                             int m1, int m2, int m3, int KH, int ci, int co, int Cp,
-                                                            const int* __restrict__ ft, const int* __restrict__ fh) {
+                                                            const int* __restrict__ ft, const int* __restrict__ fh,
+                                                            int m3s, int kw0) {  // source W modes, first one taken
   extern __shared__ float tile[];  // [Cp][2*m3 + 1]
   const int slot = blockIdx.x, i = blockIdx.y;
   const int khs = slot % KH, kts = slot / KH;
@@ -37,12 +38,12 @@ __global__ void __launch_bounds__(256) pack_spectral_kernel(Corners c, float* __
       const bool t_hi = fT >= Tp - m1;
       const int x = t_hi ? fT - (Tp - m1) : fT;
       src = c.w[(h_hi ? 2 : 0) + (t_hi ? 1 : 0)];
-      row_stride = (size_t)m1 * m2 * m3 * 2;
-      base = ((size_t)i * co * m1 * m2 + (size_t)x * m2 + y) * m3 * 2;
+      row_stride = (size_t)m1 * m2 * m3s * 2;
+      base = ((size_t)i * co * m1 * m2 + (size_t)x * m2 + y) * m3s * 2 + (size_t)kw0 * 2;
     } else {
       src = c.w[h_hi ? 1 : 0];
-      row_stride = (size_t)m2 * m3 * 2;
-      base = ((size_t)i * co * m2 + y) * m3 * 2;
+      row_stride = (size_t)m2 * m3s * 2;
+      base = ((size_t)i * co * m2 + y) * m3s * 2 + (size_t)kw0 * 2;
     }
   }
   for (int idx = threadIdx.x; idx < Cp * W2; idx += blockDim.x) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) pack_spectral_kernel(Corners c, float* __
 }
 
 int launch_pack_spectral(const float* const* corners, int ncorner, float* Wpk, const Geom& g, int ci, int co, int m1,
-                         int m2, const int* d_ft, const int* d_fh, cudaStream_t st) {
+                         int m2, const int* d_ft, const int* d_fh, cudaStream_t st, int m3_src, int kw0) {
   Corners c{};
   for (int i = 0; i < ncorner; ++i) c.w[i] = corners[i];
   const size_t smem = (size_t)g.Cp * (2 * g.m3 + 1) * sizeof(float);
@@ -68,7 +69,7 @@ int launch_pack_spectral(const float* const* corners, int ncorner, float* Wpk, c
   }
   B2_CUDA(cudaFuncSetAttribute(pack_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_spectral_kernel<<<dim3(g.KT * g.KH, g.Cp), 256, smem, st>>>(c, Wpk, g.ndim, g.Tp, g.Hp, m1, m2, g.m3, g.KH, ci, co,
-                                                                   g.Cp, d_ft, d_fh);
+                                                                   g.Cp, d_ft, d_fh, m3_src > 0 ? m3_src : g.m3, kw0);
   B2_LAUNCHED("pack_spectral_kernel");
   return 0;
 }

@@ -54,7 +54,8 @@ static void inv_complex(std::vector<float>& L, int ld, const std::vector<int>& f
     }
 }
 
-int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6]) {
+int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<float> (&host)[6], int kw0) {
+  // kw0: first kept W frequency of this table set (0 unless the plan splits modes3 > 32 into slices, api.cu)
   t->fh = kept(g.Hp, m2);
   t->ft = (g.ndim == 3) ? kept(g.Tp, m1) : std::vector<int>{0};
   const int KH = (int)t->fh.size(), KT = (int)t->ft.size();
@@ -74,8 +75,8 @@ int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<fl
   // forward W (real -> complex): rows m = ri*m3 + kw
   for (int kw = 0; kw < m3; ++kw)
     for (int w = 0; w < Wp; ++w) {
-      LF[(size_t)(0 * m3 + kw) * t->ldLF + w] = (float)tw_cos(kw, w, Wp);
-      LF[(size_t)(1 * m3 + kw) * t->ldLF + w] = (float)-tw_sin(kw, w, Wp);
+      LF[(size_t)(0 * m3 + kw) * t->ldLF + w] = (float)tw_cos(kw0 + kw, w, Wp);
+      LF[(size_t)(1 * m3 + kw) * t->ldLF + w] = (float)-tw_sin(kw0 + kw, w, Wp);
     }
   fwd_complex(LH, t->ldLH, t->fh, Hp);
   inv_complex(LHi, t->ldLHi, t->fh, Hp);
@@ -87,18 +88,19 @@ int compute_tables_host(const Geom& g, int m1, int m2, Tables* t, std::vector<fl
   const double scale = 1.0 / ((double)Wp * Hp * (g.ndim == 3 ? Tp : 1));
   for (int w = 0; w < Wp; ++w)
     for (int kw = 0; kw < m3; ++kw) {
-      const bool self_conj = (kw == 0) || (Wp % 2 == 0 && kw == Wp / 2);
+      const int fw = kw0 + kw;
+      const bool self_conj = (fw == 0) || (Wp % 2 == 0 && fw == Wp / 2);
       const double c = self_conj ? 1.0 : 2.0;
-      Gt[(size_t)w * g.K2p + 0 * m3 + kw] = (float)(c * scale * tw_cos(kw, w, Wp));
-      Gt[(size_t)w * g.K2p + 1 * m3 + kw] = (float)(-c * scale * tw_sin(kw, w, Wp));
+      Gt[(size_t)w * g.K2p + 0 * m3 + kw] = (float)(c * scale * tw_cos(fw, w, Wp));
+      Gt[(size_t)w * g.K2p + 1 * m3 + kw] = (float)(-c * scale * tw_sin(fw, w, Wp));
     }
   host[0].swap(LF), host[1].swap(LH), host[2].swap(LT), host[3].swap(LTi), host[4].swap(LHi), host[5].swap(Gt);
   return 0;
 }
 
-int build_tables(const Geom& g, int m1, int m2, Tables* t) {
+int build_tables(const Geom& g, int m1, int m2, Tables* t, int kw0) {
   std::vector<float> host[6];
-  B2_TRY(compute_tables_host(g, m1, m2, t, host));
+  B2_TRY(compute_tables_host(g, m1, m2, t, host, kw0));
   {  // forward-W table as 3xTF32 planes for the tensor-core kernel: [hi|lo][K2m][wpad], zero padded (K2m = K2 rounded
      // up to 16, the MMA N step)
     const int wpad = 2 * ceil_div(g.Wp, 64) * 32, K2m = round_up(g.K2, 16);

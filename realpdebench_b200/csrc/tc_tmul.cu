@@ -220,7 +220,7 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
   // Measured on B200: the transposed scheme wins for long contractions with few output rows (forward H: 25 ->
   // 19 us at C2, 8.9 -> 5.7 ms per rollout in 3-D) and loses for the short-K inverse transforms, where a work
   // item is a single chunk and the streamed table outweighs the data; those stay on the FFMA kernel.
-  if (N % 128 != 0 || M < 1 || M > 128 || K <= TM_CH) return 0;
+  if (N % 128 != 0 || M < 1 || M > 1024 || K <= TM_CH) return 0;  // M > 128: several 128-row m tiles (forward H at C5 k >= 48: 2 * KH = 192 / 256; inverse H: 2 * Hp rows)
   // m tile: a multiple of 16 up to 128; small M in one tile, large M in 128-row tiles
   const int MT = M <= 128 ? round_up(M, 16) : 128;
   tp->M = M, tp->K = K, tp->N = N, tp->MT = MT, tp->n_mt = ceil_div(M, MT), tp->Mpad = tp->n_mt * MT;

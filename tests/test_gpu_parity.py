@@ -235,8 +235,40 @@ def test_c5_mode_sweep_2d(R, k):
     m = m.to(dev()).eval()
     x = torch.randn(2, *s)
     y = m(x.to(dev())).cpu()
-    assert m.engine.resolved_impl() == ("tc" if k <= 32 else "simt")
+    assert m.engine.resolved_impl() == "tc"  # k = 48 / 64: two mode slices of 24 / 32 on the same kernels (api.cu: ModeSlice)
+    si = m.engine.stage_impls()
+    assert all(si[s] == "tc" for s in ("lift", "fwdW", "fwdH", "modes", "layer", "proj")), si
     assert O.rel_l2(y, O.fno2d_forward(sd, x, s)) < TOL
+
+
+@pytest.mark.parametrize("ndim,modes,s", [
+    (2, (12, 48), (2, 60, 250, 3)),      # two slices of 24 W modes
+    (2, (16, 64), (1, 60, 250, 2)),      # two slices of 32
+    (3, (2, 4, 48), (4, 10, 122, 2)),    # FNO3d: W' = 128, m3 = 48 of 65 bins
+])
+def test_mode_slices_with_amplified_spectral_branch(R, ndim, modes, s):
+    """modes3 in (32, 64] at width 64 runs as two mode slices on the tensor-core kernels (api.cu: ModeSlice), the second
+    with a frequency offset in its DFT tables and its own packed weights.  With reference-initialised weights the spectral
+    branch is < 1e-3 of the output, so a wrong offset would pass a 1e-5 whole-network check: amplify it."""
+    torch.manual_seed(77)
+    sd = O.init_state(ndim, modes, 3, 64, s, s)
+    O.randomize_bn(sd, 8)
+    sd0 = {k: (v * 0.0 if k.startswith("spectral_convs.") else v.clone()) for k, v in sd.items()}
+    sd = {k: (v * 300.0 if k.startswith("spectral_convs.") else v) for k, v in sd.items()}
+    m = (R.FNO3d if ndim == 3 else R.FNO2d)(*modes, 3, 64, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    x = torch.randn(3, *s)
+    fwd = O.fno3d_forward if ndim == 3 else O.fno2d_forward
+    with torch.no_grad():
+        ref, ref0 = fwd(sd, x, s), fwd(sd0, x, s)
+    assert O.rel_l2(ref0, ref) > 0.05
+    y = m(x.to(dev())).cpu()
+    si = m.engine.stage_impls()
+    assert m.engine.resolved_impl() == "tc" and si["layer"] == "tc" and si["fwdW"] == "tc", si
+    assert O.rel_l2(y, ref) < 2e-5   # two layer passes per layer: twice the fp32 rounding of the single-pass kernels
+    m.set_impl("simt")
+    assert O.rel_l2(m(x.to(dev())).cpu(), ref) < 2e-5
 
 
 def test_c3_fsi_width128_2d_forward(R):
