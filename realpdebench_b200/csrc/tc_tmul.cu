@@ -220,9 +220,12 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
   // Measured on B200: the transposed scheme wins for long contractions with few output rows (forward H: 25 ->
   // 19 us at C2, 8.9 -> 5.7 ms per rollout in 3-D) and loses for the short-K inverse transforms, where a work
   // item is a single chunk and the streamed table outweighs the data; those stay on the FFMA kernel.
-  if (N % 128 != 0 || M < 1 || M > 1024 || K <= TM_CH) return 0;  // M > 128: several 128-row m tiles (forward H at C5 k >= 48: 2 * KH = 192 / 256; inverse H: 2 * Hp rows)
-  // m tile: a multiple of 16 up to 128; small M in one tile, large M in 128-row tiles
-  const int MT = M <= 128 ? round_up(M, 16) : 128;
+  // (round 2, measured again with 128-row m tiles available: short-K inverse H on this kernel - C2: 2.0 -> 3.15 ms per
+  // rollout, 3-D cylinder: 10.1 -> 19.1 ms - still loses; K <= 64 stays on the FFMA kernel.)
+  if (N % 128 != 0 || M < 1 || M > 1024 || K <= TM_CH) return 0;
+  // m tiles: as few as fit 128 accumulator columns, rows balanced over them (M = 140 -> 2 x 80, not 128 + 12)
+  const int n_mt0 = ceil_div(M, 128);
+  const int MT = round_up(ceil_div(M, n_mt0), 16);
   tp->M = M, tp->K = K, tp->N = N, tp->MT = MT, tp->n_mt = ceil_div(M, MT), tp->Mpad = tp->n_mt * MT;
   tp->nchunk = ceil_div(K, TM_CH), tp->Kpad = tp->nchunk * TM_CH;
   tp->stage_bytes = TM_XS + round_up(4 * MT * 128, 1024);
