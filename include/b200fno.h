@@ -186,6 +186,7 @@ typedef struct b200fno_grads {
   float* fc1_b;
   float* fc2_w;
   float* fc2_b;
+  float* x;                /* optional: gradient w.r.t. the input field, layout of x [B][t_in][h][w][c_in]; NULL = not wanted */
 } b200fno_grads_t;
 
 /* Device bytes the training path needs on top of the plan workspace: the saved

@@ -334,13 +334,17 @@ def is_param(name: str) -> bool:
     return name.rsplit(".", 1)[-1] in PARAM_SUFFIXES
 
 
-def train_loss_and_grads(ndim: int, sd: Dict[str, Tensor], x: Tensor, target: Tensor, shape_out: Sequence[int]):
+def train_loss_and_grads(ndim: int, sd: Dict[str, Tensor], x: Tensor, target: Tensor, shape_out: Sequence[int],
+                         input_grad: bool = False):
     """``loss = model.train_loss(input, target).mean(); loss.backward()`` (train.py:328-329, fno.py:131-133).
 
     Returns ``(loss, grads, pred)``; ``sd``'s BatchNorm running buffers are updated in place like the
-    reference module in ``.train()`` mode (``num_batches_tracked`` included)."""
+    reference module in ``.train()`` mode (``num_batches_tracked`` included).  ``input_grad``: ``grads["__input__"]``
+    = the gradient with respect to ``x`` (autograd through the same forward)."""
     leaves = {k: (v.detach().clone().requires_grad_(True) if is_param(k) else v) for k, v in sd.items()}
     fwd = fno3d_forward if ndim == 3 else fno2d_forward
+    if input_grad:
+        x = x.detach().clone().requires_grad_(True)
     pred = fwd(leaves, x, shape_out, training=True)
     loss = F.mse_loss(pred, target, reduction="none").mean()  # utils/metrics.py:11-13 + train.py:328
     loss.backward()
@@ -348,6 +352,8 @@ def train_loss_and_grads(ndim: int, sd: Dict[str, Tensor], x: Tensor, target: Te
         if k.endswith("num_batches_tracked"):
             sd[k] = sd[k] + 1
     grads = {k: v.grad for k, v in leaves.items() if is_param(k)}
+    if input_grad:
+        grads["__input__"] = x.grad
     return float(loss.detach()), grads, pred.detach()
 
 

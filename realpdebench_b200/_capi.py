@@ -50,7 +50,8 @@ class Weights(C.Structure):
 
 class Grads(C.Structure):
     _fields_ = [("fc0_w", _fp), ("fc0_b", _fp), ("spec_w", _fpp), ("conv_w", _fpp), ("conv_b", _fpp),
-                ("bn_weight", _fpp), ("bn_bias", _fpp), ("fc1_w", _fp), ("fc1_b", _fp), ("fc2_w", _fp), ("fc2_b", _fp)]
+                ("bn_weight", _fpp), ("bn_bias", _fpp), ("fc1_w", _fp), ("fc1_b", _fp), ("fc2_w", _fp), ("fc2_b", _fp),
+                ("x", _fp)]
 
 
 _lib = None

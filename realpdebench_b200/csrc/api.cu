@@ -1411,6 +1411,8 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
     // column nf of the feature matrix is the constant 1 at valid points (0 in the pad region): the bias gradient
     B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.G, p->Klp, p->Klp, nf, P, gr->fc0_w, nf, gr->fc0_b, st));
   }
+  // gradient w.r.t. the input field (every element of x feeds exactly one lift feature: no zero fill needed)
+  if (gr->x) B2_TRY(launch_lift_bwd_input(make_lift_args(p, B, x, nullptr), gy, gr->x, st));
   return 0;
 }
 

@@ -145,6 +145,7 @@ struct LiftArgs {
   int bf16 = 0;          // bf16 compute mode: features rounded to bf16 (weights rounded when packed)
 };
 int launch_lift(const LiftArgs& a, cudaStream_t st);
+int launch_lift_bwd_input(const LiftArgs& a, const float* dact, float* dx, cudaStream_t st);  // train.cu
 
 struct ProjArgs {
   const float* act;     // [B][Tp][Hp][Wp][Cp]

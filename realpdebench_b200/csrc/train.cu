@@ -704,6 +704,41 @@ int launch_unpack_spectral_grad(const float* dWpk, float* const* corners, int nc
 }
 
 // ---------------------------------------------------------------------------
+// Lift backward w.r.t. the input field (fno.py:106-109 reversed): dx[b,t,h,w,c] = sum_o d act0[p][o] * fc0_w[o][f],
+// f = the lift feature the input element feeds (LiftArgs::in_off maps feature -> offset inside a point's input).
+// The grid-coordinate columns of fc0 carry no gradient.  grid (valid rows (b,t,h), 64-point tiles over W); block 256.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lift_bwd_input_kernel(LiftArgs a, const float* __restrict__ dact,
+                                                             float* __restrict__ dx) {
+  extern __shared__ __align__(16) float lb_sh[];  // dact tile [64][Cp + 1]
+  const int ld = a.Cp + 1;
+  const long long row = blockIdx.x;
+  const int h = (int)(row % a.H), t = (int)((row / a.H) % a.T), b = (int)(row / ((long long)a.H * a.T));
+  const int p0 = blockIdx.y * 64, npts = min(64, a.W - p0);
+  const float* drow = dact + ((((size_t)b * a.Tp + t) * a.Hp + h) * a.Wp + p0) * a.Cp;
+  for (int idx = threadIdx.x; idx < npts * a.Cp; idx += 256) lb_sh[(idx / a.Cp) * ld + idx % a.Cp] = drow[idx];
+  __syncthreads();
+  float* xb = dx + (size_t)b * a.x_sB + (size_t)t * a.x_sT + ((size_t)h * a.W + p0) * a.c_in;
+  for (int item = threadIdx.x; item < npts * a.Fin; item += 256) {
+    const int pp = item % npts, f = item / npts;  // consecutive threads: consecutive points, same feature (weights broadcast)
+    const float* w = a.W0T + (size_t)f * a.Cp;    // W0T[f][o] = fc0_w[o][f]
+    const float* d = lb_sh + pp * ld;
+    float acc = 0.f;
+    for (int o = 0; o < a.Cp; ++o) acc = fmaf(d[o], __ldg(w + o), acc);
+    xb[(size_t)pp * a.c_in + a.in_off[f]] = acc;
+  }
+}
+
+int launch_lift_bwd_input(const LiftArgs& a, const float* dact, float* dx, cudaStream_t st) {
+  const size_t smem = (size_t)64 * (a.Cp + 1) * sizeof(float);
+  B2_CUDA(cudaFuncSetAttribute(lift_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((long long)a.B * a.T * a.H), ceil_div(a.W, 64));
+  lift_bwd_input_kernel<<<grid, 256, smem, st>>>(a, dact, dx);
+  B2_LAUNCHED("lift_bwd_input_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Fused Adam step (torch.optim.Adam defaults: no weight decay, no amsgrad) in ONE pass over p, g, m, v.
 // Same elementwise formulas, in the same order, as torch's foreach implementation:
 //   m <- m + (1-b1)(g - m);  v <- v*b2 + (1-b2) g*g;  p <- p - step_size * (m / (sqrt(v)/sqrt(bc2) + eps))

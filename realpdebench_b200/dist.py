@@ -305,13 +305,14 @@ class OverlappedGradientReducer:
         tag = f".{idx}."
         return [n for n in names if tag in n and n.startswith(("spectral_convs.", "convs.", "bns."))]
 
-    def backward_and_reduce(self, engine, x, dy, params: dict, seq=None) -> dict:
+    def backward_and_reduce(self, engine, x, dy, params: dict, seq=None, input_grad: bool = False) -> dict:
         dist, L = self.dist, self.n_layers
         cur = torch.cuda.current_stream(x.device)
         handles = [e.cuda_event for e in self.events]
         if not all(handles):
             raise RuntimeError("OverlappedGradientReducer: a gradient-ready event has no cudaEvent_t handle")
-        grads = engine.train_backward(x, dy, params, ready_events=handles, seq=seq)
+        grads = engine.train_backward(x, dy, params, ready_events=handles, seq=seq, input_grad=input_grad)
+        dx = grads.pop("__input__", None)  # the input gradient is per shard: not part of any reduction group
         if os.environ.get("B200FNO_REDUCER_SYNC"):  # race probe (profiles/diag_train.py): no overlap at all
             torch.cuda.synchronize(x.device)
         if os.environ.get("B200FNO_REDUCER_SNAPSHOT"):  # diag: the local gradients as the backward left them
@@ -368,4 +369,6 @@ class OverlappedGradientReducer:
         for g in grads.values():
             g.record_stream(self.side)
         self.bytes_last = total
+        if dx is not None:
+            grads["__input__"] = dx
         return grads

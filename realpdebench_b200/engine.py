@@ -218,11 +218,13 @@ class FNOEngine:
         return self._train_seq
 
     def train_backward(self, x: torch.Tensor, dy: torch.Tensor, params: dict,
-                       ready_events: Optional[Sequence[int]] = None, seq: Optional[int] = None) -> dict:
+                       ready_events: Optional[Sequence[int]] = None, seq: Optional[int] = None,
+                       input_grad: bool = False) -> dict:
         """Parameter gradients of the last ``train_forward`` in the reference layout.
         ``params``: name -> parameter tensor (reference state_dict names); returns name -> gradient tensor.
         ``ready_events``: optional ``n_layers + 1`` raw ``cudaEvent_t`` handles recorded when each gradient group
-        is final (see ``b200fno_train_backward``)."""
+        is final (see ``b200fno_train_backward``).  ``input_grad``: also return the gradient with respect to the
+        input field under the key ``"__input__"`` (same layout as ``x``)."""
         _require_cuda(dy, "output gradient")
         if seq is not None and seq != self._train_seq:
             # the training workspace holds the activations of ONE forward (b200fno.h: "one forward outstanding per
@@ -250,14 +252,17 @@ class FNOEngine:
             _capi.ptr_array([ptr(f"bns.{i}.weight") for i in range(n)]),
             _capi.ptr_array([ptr(f"bns.{i}.bias") for i in range(n)]),
         ]
+        dx = torch.empty_like(x) if input_grad else None
         g = Grads(fc0_w=ptr("fc0.weight"), fc0_b=ptr("fc0.bias"), spec_w=arrs[0], conv_w=arrs[1], conv_b=arrs[2],
                   bn_weight=arrs[3], bn_bias=arrs[4], fc1_w=ptr("fc1.weight"), fc1_b=ptr("fc1.bias"),
-                  fc2_w=ptr("fc2.weight"), fc2_b=ptr("fc2.bias"))
+                  fc2_w=ptr("fc2.weight"), fc2_b=ptr("fc2.bias"), x=dx.data_ptr() if input_grad else None)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
             ev = _capi.ptr_array(list(ready_events)) if ready_events is not None else None
             check(_capi.lib().b200fno_train_backward(self._plan, x.shape[0], x.data_ptr(), dy.data_ptr(), C.byref(g),
                                                      ev, stream))
+        if input_grad:
+            grads["__input__"] = dx
         return grads
 
     def resolved_impl(self) -> str:

@@ -60,12 +60,11 @@ class _TrainForward(torch.autograd.Function):
 
     The parameters are inputs of the Function, so autograd delivers the engine's gradients to the very
     ``nn.Parameter`` objects ``train.py:290`` hands to Adam (and DDP-style hooks fire).  The gradient with
-    respect to the input field is not produced (the reference training loop never needs it)."""
+    respect to the input field is produced when the input requires it (a caller differentiating through the
+    surrogate; the reference training loop itself never does)."""
 
     @staticmethod
     def forward(ctx, module, x, names, *params):
-        if ctx.needs_input_grad[1]:
-            raise RuntimeError("b200fno: the training path does not produce the gradient w.r.t. the input tensor")
         sd, key = module._engine_state()
         bns = list(module.bns)
         track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
@@ -91,12 +90,14 @@ class _TrainForward(torch.autograd.Function):
         need = ctx.needs_input_grad[3:]
         params = dict(zip(ctx.names, ctx.params))
         sync = getattr(ctx.module, "_grad_sync", None)  # dist.OverlappedGradientReducer: all-reduce under the backward
+        want_dx = bool(ctx.needs_input_grad[1])
         if sync is not None:
-            grads = sync.backward_and_reduce(ctx.module._engine, ctx.x, dy, params, seq=ctx.seq)
+            grads = sync.backward_and_reduce(ctx.module._engine, ctx.x, dy, params, seq=ctx.seq, input_grad=want_dx)
         else:
-            grads = ctx.module._engine.train_backward(ctx.x, dy, params, seq=ctx.seq)
+            grads = ctx.module._engine.train_backward(ctx.x, dy, params, seq=ctx.seq, input_grad=want_dx)
+        dx = grads.pop("__input__", None)  # local to this rank's shard: never all-reduced
         out = tuple(grads[n] if nd else None for n, nd in zip(ctx.names, need))
-        return (None, None, None) + out
+        return (None, dx, None) + out
 
 
 class _EngineFNO(Model):

@@ -162,11 +162,38 @@ def test_weighted_output_gradient(R):
 def test_train_mode_errors(R):
     ctor = (2, 3, 3, 1, 8, (3, 7, 9, 2), (3, 7, 9, 2))
     m = R.FNO3d(*ctor).to(dev()).train()
-    x = torch.randn(2, *ctor[5], device=dev(), requires_grad=True)
-    with pytest.raises(RuntimeError, match="input"):
-        m(x)
+    x = torch.randn(2, *ctor[5], device=dev())
     with pytest.raises(RuntimeError, match="eval"):
-        m.rollout(x.detach(), torch.ones(2, device=dev()), torch.zeros(2, device=dev()), 1)
+        m.rollout(x, torch.ones(2, device=dev()), torch.zeros(2, device=dev()), 1)
+
+
+@pytest.mark.parametrize("ndim,ctor,batch", [
+    (3, (2, 3, 3, 2, 8, (3, 7, 9, 2), (3, 7, 9, 2)), 2),          # FNO3d: feature = channel
+    (3, (2, 3, 4, 1, 8, (4, 8, 12, 5), (4, 8, 12, 3)), 2),        # controlled: parameter channels get a gradient too
+    (2, (5, 6, 2, 12, (4, 20, 28, 3), (4, 20, 28, 3)), 3),        # FNO2d: frames folded into the features
+    (2, (4, 5, 2, 128, (2, 9, 10, 2), (2, 9, 10, 2)), 20),        # width 128
+])
+def test_input_gradient_matches_oracle_autograd(R, ndim, ctor, batch):
+    """Gradient with respect to the input field (a caller that differentiates through the surrogate; VERDICT r01
+    missing item 7): ``x.grad`` after ``loss.backward()`` against autograd through the oracle forward, and the parameter
+    gradients of the same backward are unchanged."""
+    torch.manual_seed(12)
+    m = (R.FNO3d if ndim == 3 else R.FNO2d)(*ctor)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    O.randomize_bn(sd, 19)
+    m.load_state_dict(sd)
+    m = m.to(dev()).train()
+    s_in, s_out = ctor[-2], ctor[-1]
+    x, t = torch.randn(batch, *s_in), torch.randn(batch, *s_out)
+    loss_ref, grads_ref, _ = O.train_loss_and_grads(ndim, sd, x, t, s_out, input_grad=True)
+    xd = x.to(dev()).requires_grad_(True)
+    loss = m.train_loss(xd, t.to(dev())).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref) < 1e-5 * abs(loss_ref)
+    dx_ref = grads_ref.pop("__input__")
+    assert xd.grad is not None and xd.grad.shape == x.shape
+    assert O.rel_l2(xd.grad.cpu(), dx_ref) < 2e-5
+    check_grads(m, grads_ref)
 
 
 # ---------------------------------------------------------------- BASELINE config C3 shape (fsi, width 128)
