@@ -274,7 +274,7 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r
 // no-op), lo = x - hi exact in fp32 and signed, |lo| <= 2^-11 |x|.  With a truncated hi (what the MMA would make of the raw
 // fp32 value) lo is one-signed and twice as large, and the dropped lo*lo term becomes a coherent bias: one spectral
 // convolution then carries 1.0e-6 relative error against 1.4e-7 with the rounded split (plain fp32 FFMA: 4e-7;
-// scripts_tmp/split_study.py).
+// profiles/split_study.py).
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t u) { return (u + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(tf32_rn_bits(__float_as_uint(x))); }
 

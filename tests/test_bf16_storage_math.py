@@ -1,11 +1,11 @@
-"""Precision study for the bf16 variant BASELINE config C3 names (north_star: 1e-2 relative L2 in bf16).
+"""CPU design study for the NEXT step of the bf16 mode (bf16 activation STORAGE) - not a test of shipped kernels.
 
-The reference's only working bf16 path is ``torch.autocast``: Linear / Conv run in bf16, FFT and the complex
-einsum stay fp32, the output is bf16.  The engine's planned bf16 mode is different and cheaper for an HBM-bound path:
-keep every GEMM in fp32 (3xTF32) and the spectral stages in fp32, but STORE the activations that cross HBM between
-kernels (lift output, each layer's output) as bf16 - halving the `L * 2 * C * T'H'W'` term of SURVEY 8d.  This test
-emulates that on the CPU oracle and checks that it stays inside the bf16 tolerance against both the fp32 reference and
-the reference under autocast, i.e. that the design can meet the parity bar before any kernel is written.
+What is built (round 2, DESIGN section 3e, GPU parity in tests/test_gpu_bf16.py) is the reference's own bf16 arithmetic:
+``torch.autocast`` semantics - Linear / Conv operands in bf16 with fp32 accumulation, FFT and the complex einsum in
+fp32, tensors between the kernels still fp32.  The lever that is left on the HBM-bound kernels is to additionally STORE the
+activations that cross HBM between kernels (lift output, each layer's output) as bf16 - halving the `L * 2 * C * T'H'W'` term
+of SURVEY 8d.  This file emulates that on the CPU oracle and checks that it stays inside the bf16 tolerance against both the
+fp32 reference and the reference under autocast, i.e. that the design can meet the parity bar before any kernel is written.
 """
 import pytest
 import torch
