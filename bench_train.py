@@ -86,6 +86,8 @@ def run_engine(args):
     ndim, modes, L, width, s_in, s_out, B = WORKLOADS[args.workload]
     B = args.batch or B
     model = build_model(R, ndim, modes, L, width, s_in, s_out).to(dev).train()
+    if args.dtype == "bf16":  # BASELINE config C3 as named: the autocast arithmetic (GEMM operands in bf16, fp32 accumulate)
+        model.set_compute("bf16")
     if args.fused_adam:  # same updates in one pass per parameter (realpdebench_b200/optim.py)
         from realpdebench_b200.optim import FusedAdam
         optimizer = FusedAdam(model.parameters(), lr=1e-3)
@@ -160,7 +162,7 @@ def run_engine(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "field-points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.workload, B, world),
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config(args.workload, B, world),
             "impl": "b200fno", "samples_per_sec": world * B / (ms_step * 1e-3),
             "e2e": {"value": world * pts / (e2e_ms * 1e-3), "unit": "field-points/s",
                     "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
@@ -187,6 +189,9 @@ def main():
     ap.add_argument("--impl", default="b200fno", choices=["b200fno", "reference"])
     ap.add_argument("--workload", default="fno2d_fsi_64x64_train", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16 = torch.autocast(bfloat16) arithmetic of the reference for every Linear / Conv GEMM of the "
+                         "step (forward + backward); FFMA kernels either way, so this is the numerics, not a speed-up")
     ap.add_argument("--fused-adam", action="store_true", help="realpdebench_b200.optim.FusedAdam instead of torch's Adam")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of under it")
     ap.add_argument("--overlap", action="store_true", help="force the overlapped all-reduce also beyond 4 ranks")

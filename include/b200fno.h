@@ -114,7 +114,9 @@ int b200fno_plan_set_impl(b200fno_plan_t* plan, int impl);
 /* Which implementation the layer kernels resolve to (B200FNO_IMPL_SIMT|TC). */
 int b200fno_plan_get_impl(const b200fno_plan_t* plan);
 /* Arithmetic of the Linear / Conv products (B200FNO_COMPUTE_*).  May be changed at any time; a change invalidates the
- * packed weights (call b200fno_pack_weights again).  The training entry points require B200FNO_COMPUTE_F32. */
+ * packed weights (call b200fno_pack_weights again).  The training entry points honour it too: both operands of every
+ * Linear / Conv GEMM of the forward AND the backward pass are rounded to bf16 (autocast's backward), fp32 accumulation;
+ * the arithmetic of the mode, not its speed - the training kernels are FFMA kernels either way. */
 int b200fno_plan_set_compute(b200fno_plan_t* plan, int compute);
 int b200fno_plan_get_compute(const b200fno_plan_t* plan);
 

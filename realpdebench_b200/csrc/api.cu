@@ -707,6 +707,10 @@ int b200fno_pack_weights(b200fno_plan_t* p, const b200fno_weights_t* w, void* st
     B2_TRY(launch_round_bf16(p->W0T, (size_t)p->Klp * g.Cp, st));
     B2_TRY(launch_round_bf16(p->fc1T, (size_t)g.Cp * 128, st));
     B2_TRY(launch_round_bf16(p->fc2T, (size_t)128 * p->Fp, st));
+    // training copies (backward GEMMs: grad_input = grad_output . W with W as a bf16 tensor)
+    for (auto& L : p->layers) B2_TRY(launch_round_bf16(L.convW, (size_t)g.Cp * g.Cp, st));
+    B2_TRY(launch_round_bf16(p->fc1W, (size_t)128 * g.Cp, st));
+    B2_TRY(launch_round_bf16(p->fc2W, (size_t)p->Fp * 128, st));
   }
   p->weights_ready = true;
   return 0;
@@ -1246,10 +1250,6 @@ int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, floa
     set_error("b200fno_train_bind must be called before b200fno_train_forward");
     return B200FNO_ESTATE;
   }
-  if (p->bf16) {
-    set_error("the training path computes in fp32 only (B200FNO_COMPUTE_BF16 covers the evaluation forward / rollout)");
-    return B200FNO_ESTATE;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
@@ -1263,7 +1263,7 @@ int b200fno_train_forward(b200fno_plan_t* p, int32_t batch, const float* x, floa
     B2_TRY(run_spectral(g, p->tab, B, tr.xs[l], Lp.spec, p->bufAD, p->bufBC, tr.Ssave[l], p->bufO, st));
     // z = conv1x1(x) + bias + irfft_W(D)   (fno.py:114-116), BatchNorm and GELU follow as separate passes
     B2_TRY(launch_layer(tr.xs[l], tr.zs[l], Lp.convT, p->tab.Gt, p->bufAD, nullptr, Lp.cbias, rows, g.Wp, g.Cp, g.K2,
-                        g.K2p, 0, st));
+                        g.K2p, 0, st, p->bf16));
     B2_TRY(launch_colstats(tr.zs[l], P, g.Cp, tr.stats, st));
     B2_TRY(launch_bn_finalize(tr.stats, P, d.bn_eps, Lp.gamma, Lp.beta, C, g.Cp, tr.bnc[l],
                               bn_running_mean ? bn_running_mean[l] : nullptr,
@@ -1329,7 +1329,7 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   pb.act = tr.xs[L], pb.dy = dy, pb.fc1T = p->fc1T, pb.fc1b = p->fc1b, pb.fc2W = p->fc2W, pb.fc1W = p->fc1W;
   pb.out_off = p->out_off, pb.G = tr.G, pb.dH = tr.dH, pb.dF = tr.dF, pb.dact = tr.g0;
   pb.B = B, pb.T = p->Tv, pb.H = d.h, pb.W = d.w, pb.Tp = g.Tp, pb.Hp = g.Hp, pb.Wp = g.Wp, pb.Cp = Cp;
-  pb.Fout = p->Fout, pb.Fp = p->Fp, pb.c_out = d.c_out;
+  pb.Fout = p->Fout, pb.Fp = p->Fp, pb.c_out = d.c_out, pb.bf16 = p->bf16;
   const long long HW = (long long)d.h * d.w;
   pb.out_sB = (long long)d.t_out * HW * d.c_out;
   pb.out_sT = d.ndim == 3 ? (long long)(d.t_out / d.t_in) * HW * d.c_out : 0;
@@ -1337,9 +1337,9 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
   B2_TRY(launch_proj_bwd(pb, st));
   B2_TRY(chk(2, tr.g0, (size_t)P * Cp));
   B2_TRY(chk(3, tr.dH, (size_t)P * 128));
-  if (gr->fc2_w) B2_TRY(launch_wgrad(tr.dF, p->Fp, p->Fp, p->Fout, tr.G, 128, 128, 128, P, gr->fc2_w, 128, nullptr, st));
+  if (gr->fc2_w) B2_TRY(launch_wgrad(tr.dF, p->Fp, p->Fp, p->Fout, tr.G, 128, 128, 128, P, gr->fc2_w, 128, nullptr, st, p->bf16));
   if (gr->fc2_b) B2_TRY(launch_colsum(tr.dF, p->Fp, p->Fout, P, gr->fc2_b, st));
-  if (gr->fc1_w) B2_TRY(launch_wgrad(tr.dH, 128, 128, 128, tr.xs[L], Cp, Cp, C, P, gr->fc1_w, C, nullptr, st));
+  if (gr->fc1_w) B2_TRY(launch_wgrad(tr.dH, 128, 128, 128, tr.xs[L], Cp, Cp, C, P, gr->fc1_w, C, nullptr, st, p->bf16));
   if (gr->fc1_b) B2_TRY(launch_colsum(tr.dH, 128, 128, P, gr->fc1_b, st));
   // grads_ready[i]: caller's cudaEvent_t recorded as soon as the gradients of group i are final, so that a
   // data-parallel caller can start their all-reduce on another stream under the rest of the backward pass
@@ -1359,7 +1359,7 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
                               gr->bn_weight ? gr->bn_weight[l] : nullptr, gr->bn_bias ? gr->bn_bias[l] : nullptr, st));
     B2_TRY(chk(sid + 2, gy, (size_t)P * Cp));
     if (gr->conv_w && gr->conv_w[l])
-      B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.xs[l], Cp, Cp, C, P, gr->conv_w[l], C, nullptr, st));
+      B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.xs[l], Cp, Cp, C, P, gr->conv_w[l], C, nullptr, st, p->bf16));
     if (gr->conv_b && gr->conv_b[l]) B2_TRY(launch_colsum(gy, Cp, C, P, gr->conv_b[l], st));
     // adjoint of irfft_W, ifft_H, ifft_T: the forward kernels with transposed tables
     B2_TRY(launch_lmul(tr.GtT, tab.ldLF, g.K2, g.Wp, gy, (long long)g.Wp * Cp, Cp, p->bufAD, (long long)g.K2 * Cp, Cp, Cp,
@@ -1399,7 +1399,8 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
     // dx = dz . conv_w  +  rfft_W^T(dA): the layer kernel with the untransposed conv weight and LF^T
     B2_TRY(chk(sid + 11, p->bufAD, g.a_elems(B)));
     B2_TRY(chk(sid + 12, Lp.convW, (size_t)Cp * Cp));
-    B2_TRY(launch_layer(gy, other, Lp.convW, tr.LFT, p->bufAD, nullptr, nullptr, rows, g.Wp, Cp, g.K2, g.K2p, 0, st));
+    B2_TRY(launch_layer(gy, other, Lp.convW, tr.LFT, p->bufAD, nullptr, nullptr, rows, g.Wp, Cp, g.K2, g.K2p, 0, st,
+                        p->bf16));  // bf16 mode: dz enters the conv adjoint as a bf16 tensor, the DFT adjoint in fp32
     B2_TRY(chk(sid + 13, other, (size_t)P * Cp));
     std::swap(gy, other);
   }
@@ -1409,7 +1410,7 @@ int b200fno_train_backward(b200fno_plan_t* p, int32_t batch, const float* x, con
     B2_TRY(chk(9001, tr.G, (size_t)P * p->Klp));
     B2_TRY(chk(9002, gy, (size_t)P * Cp));
     // column nf of the feature matrix is the constant 1 at valid points (0 in the pad region): the bias gradient
-    B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.G, p->Klp, p->Klp, nf, P, gr->fc0_w, nf, gr->fc0_b, st));
+    B2_TRY(launch_wgrad(gy, Cp, Cp, C, tr.G, p->Klp, p->Klp, nf, P, gr->fc0_w, nf, gr->fc0_b, st, p->bf16));
   }
   // gradient w.r.t. the input field (every element of x feeds exactly one lift feature: no zero fill needed)
   if (gr->x) B2_TRY(launch_lift_bwd_input(make_lift_args(p, B, x, nullptr), gy, gr->x, st));

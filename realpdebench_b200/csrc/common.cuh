@@ -189,7 +189,7 @@ int launch_bn_backward(const float* gy, const float* z, float* dz, long long P, 
                        double* sums, float* d_gamma, float* d_beta, cudaStream_t st);
 // out[m*ldo+n] += sum_p A[p*lda+m] B[p*ldb+n], m < Mv, n < Nv (column Nv -> extra[m]); caller zeroes out
 int launch_wgrad(const float* A, int lda, int M, int Mv, const float* B, int ldb, int N, int Nv, long long P, float* out,
-                 int ldo, float* extra, cudaStream_t st);
+                 int ldo, float* extra, cudaStream_t st, int bf16 = 0);
 int launch_colsum(const float* A, int lda, int Nv, long long P, float* out, cudaStream_t st);
 
 struct ProjBwdArgs {
@@ -200,6 +200,7 @@ struct ProjBwdArgs {
   float *G, *dH, *dF, *dact;                 // [P][128], [P][128], [P][Fp], [P][Cp]
   int B, T, H, W, Tp, Hp, Wp, Cp, Fout, Fp, c_out;
   long long out_sB, out_sT;
+  int bf16 = 0;  // bf16 compute mode: every GEMM operand rounded to bf16 (train.cu)
 };
 int launch_proj_bwd(const ProjBwdArgs& a, cudaStream_t st);
 int launch_lift_features(const LiftArgs& a, float* feat, cudaStream_t st);

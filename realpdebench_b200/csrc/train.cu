@@ -259,13 +259,24 @@ int launch_bn_backward(const float* gy, const float* z, float* dz, long long P, 
 }
 
 // ---------------------------------------------------------------------------
+// bf16 compute mode (torch.autocast semantics: both operands of every Linear / Conv GEMM, forward AND backward, are bf16
+// tensors; accumulation fp32): round to nearest-even bf16
+__device__ __forceinline__ float tr_bf16r(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+__device__ __forceinline__ float4 tr_bf16r4(float4 v) {
+  return make_float4(tr_bf16r(v.x), tr_bf16r(v.y), tr_bf16r(v.z), tr_bf16r(v.w));
+}
+
 // wgrad: out[m*ldo + n] += sum_p A[p*lda + m] * B[p*ldb + n]      m < Mv, n < Nv
 // (column n == Nv goes to extra[m] when extra != nullptr: the lift's bias column).
 // Split over points: grid.x CTAs each own every grid.x-th chunk of 32 points; 64x64 output tile per CTA.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A, int lda, int M, int Mv,
                                                     const float* __restrict__ B, int ldb, int N, int Nv, long long P,
-                                                    float* __restrict__ out, int ldo, float* __restrict__ extra) {
+                                                    float* __restrict__ out, int ldo, float* __restrict__ extra,
+                                                    int bf16) {
   __shared__ __align__(16) float As[2][KC * 64];
   __shared__ __align__(16) float Bs[2][KC * 64];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A,
       const long long p = c * KC + kk;
       ra[i] = (p < P && m0 + cc < M) ? ldg4(A + p * lda + m0 + cc) : zero4();
       rb[i] = (p < P && n0 + cc < N) ? ldg4(B + p * ldb + n0 + cc) : zero4();
+      if (bf16) ra[i] = tr_bf16r4(ra[i]), rb[i] = tr_bf16r4(rb[i]);  // grad_output and the layer input as bf16 tensors
     }
   };
   long long c = blockIdx.x;
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A,
 }
 
 int launch_wgrad(const float* A, int lda, int M, int Mv, const float* B, int ldb, int N, int Nv, long long P, float* out,
-                 int ldo, float* extra, cudaStream_t st) {
+                 int ldo, float* extra, cudaStream_t st, int bf16) {
   if (P <= 0) return 0;
   if ((lda | ldb | M | N) & 3) {
     set_error("internal: wgrad operands must be padded to multiples of 4");
@@ -332,7 +344,7 @@ int launch_wgrad(const float* A, int lda, int M, int Mv, const float* B, int ldb
   const int tiles = ceil_div(M, 64) * ceil_div(N, 64);
   const int gx = (int)std::max<long long>(1, std::min<long long>(chunks, std::max(1, 148 * 4 / tiles)));
   dim3 grid(gx, ceil_div(M, 64), ceil_div(N, 64));
-  wgrad_kernel<<<grid, 256, 0, st>>>(A, lda, M, Mv, B, ldb, N, Nv, P, out, ldo, extra);
+  wgrad_kernel<<<grid, 256, 0, st>>>(A, lda, M, Mv, B, ldb, N, Nv, P, out, ldo, extra, bf16);
   B2_LAUNCHED("wgrad_kernel");
   return 0;
 }
@@ -413,7 +425,9 @@ __global__ void __launch_bounds__(256) proj_bwd_kernel(ProjBwdArgs a) {
     for (int i = 0; i < 2; ++i) {
       const int idx = tid + i * 256, pp = idx >> 3, kk = (idx & 7) * 4;
       const int p = p0 + pp, k = k0 + kk;
-      *reinterpret_cast<float4*>(As + pp * LDA + kk) = (p < a.Wp && k < a.Cp) ? ldg4(in_row + (size_t)p * a.Cp + k) : zero4();
+      float4 xv = (p < a.Wp && k < a.Cp) ? ldg4(in_row + (size_t)p * a.Cp + k) : zero4();
+      if (a.bf16) xv = tr_bf16r4(xv);
+      *reinterpret_cast<float4*>(As + pp * LDA + kk) = xv;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -436,8 +450,9 @@ __global__ void __launch_bounds__(256) proj_bwd_kernel(ProjBwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float v0 = acc0[r][j] + bb0[j], v1 = acc1[r][j] + bb1[j];
-        hrow[tx * 4 + j] = gelu_erf(v0), grow[tx * 4 + j] = gelu_grad(v0);
-        hrow[64 + tx * 4 + j] = gelu_erf(v1), grow[64 + tx * 4 + j] = gelu_grad(v1);
+        const float g0 = gelu_erf(v0), g1 = gelu_erf(v1);  // bf16 mode: the fc2 operand is a bf16 tensor (as in the forward)
+        hrow[tx * 4 + j] = a.bf16 ? tr_bf16r(g0) : g0, grow[tx * 4 + j] = gelu_grad(v0);
+        hrow[64 + tx * 4 + j] = a.bf16 ? tr_bf16r(g1) : g1, grow[64 + tx * 4 + j] = gelu_grad(v1);
       }
     }
   }
@@ -458,6 +473,7 @@ __global__ void __launch_bounds__(256) proj_bwd_kernel(ProjBwdArgs a) {
       const int w = p0 + pp, f = f0 + kk;
       float v = 0.f;
       if (w < a.W && f < a.Fout) v = __ldg(a.dy + pt_out + (size_t)w * a.c_out + a.out_off[f]);
+      if (a.bf16) v = tr_bf16r(v);  // grad_output of fc2 (its output is a bf16 tensor under autocast)
       As[pp * LDA + kk] = v;
       if (pp < npts && f < a.Fp) a.dF[(P0 + pp) * a.Fp + f] = v;
     }
@@ -478,8 +494,9 @@ __global__ void __launch_bounds__(256) proj_bwd_kernel(ProjBwdArgs a) {
     const float* grow = Gp + (ty * 4 + r) * LDH;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      hrow[tx * 4 + j] = acc0[r][j] * grow[tx * 4 + j];
-      hrow[64 + tx * 4 + j] = acc1[r][j] * grow[64 + tx * 4 + j];
+      const float d0 = acc0[r][j] * grow[tx * 4 + j], d1 = acc1[r][j] * grow[64 + tx * 4 + j];
+      hrow[tx * 4 + j] = a.bf16 ? tr_bf16r(d0) : d0;  // grad_output of fc1
+      hrow[64 + tx * 4 + j] = a.bf16 ? tr_bf16r(d1) : d1;
     }
   }
   __syncthreads();
@@ -716,7 +733,8 @@ __global__ void __launch_bounds__(256) lift_bwd_input_kernel(LiftArgs a, const f
   const int h = (int)(row % a.H), t = (int)((row / a.H) % a.T), b = (int)(row / ((long long)a.H * a.T));
   const int p0 = blockIdx.y * 64, npts = min(64, a.W - p0);
   const float* drow = dact + ((((size_t)b * a.Tp + t) * a.Hp + h) * a.Wp + p0) * a.Cp;
-  for (int idx = threadIdx.x; idx < npts * a.Cp; idx += 256) lb_sh[(idx / a.Cp) * ld + idx % a.Cp] = drow[idx];
+  for (int idx = threadIdx.x; idx < npts * a.Cp; idx += 256)
+    lb_sh[(idx / a.Cp) * ld + idx % a.Cp] = a.bf16 ? tr_bf16r(drow[idx]) : drow[idx];
   __syncthreads();
   float* xb = dx + (size_t)b * a.x_sB + (size_t)t * a.x_sT + ((size_t)h * a.W + p0) * a.c_in;
   for (int item = threadIdx.x; item < npts * a.Fin; item += 256) {

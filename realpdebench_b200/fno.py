@@ -122,8 +122,8 @@ class _EngineFNO(Model):
 
     def set_compute(self, compute: str):
         """'f32' (default) | 'bf16'.  'bf16' = what the reference computes under ``torch.autocast(dtype=bfloat16)``
-        (SURVEY F7): Linear / Conv operands in bf16 with fp32 accumulation, everything spectral in fp32; evaluation
-        forward and rollout only.  Inside a ``torch.autocast("cuda", dtype=torch.bfloat16)`` context the eval-mode
+        (SURVEY F7): Linear / Conv operands in bf16 with fp32 accumulation, everything spectral in fp32 - evaluation
+        forward, rollout and the training step (forward + backward GEMMs).  Inside a ``torch.autocast("cuda", dtype=torch.bfloat16)`` context the eval-mode
         forward selects it by itself (and returns a bf16 tensor, as the reference module does)."""
         self._compute = compute
         self._engine.set_compute(compute)
@@ -152,9 +152,11 @@ class _EngineFNO(Model):
             self._engine.set_compute(compute)
             y = self._engine.forward(x.float() if autocast else x, sd, key)
             return y.to(torch.bfloat16) if autocast else y  # fc2 is a Linear: bf16 output under autocast
-        if compute != "f32":
-            raise RuntimeError("b200fno: the training path computes in fp32 only; the bf16 (autocast) mode covers the "
-                               "evaluation forward and the rollout")
+        # train mode: the same switch (bf16: every Linear / Conv GEMM of forward and backward on bf16-rounded operands);
+        # the output stays fp32 (autocast would hand the loss a bf16 tensor and cast it straight back to fp32)
+        self._engine.set_compute(compute)
+        if autocast:
+            x = x.float()
         # train mode (train.py:325-329): batch-statistics BatchNorm; differentiable w.r.t. every parameter
         names = [k for k, _ in self.named_parameters()]
         return _TrainForward.apply(self, x, names, *[sd[k] for k in names])
