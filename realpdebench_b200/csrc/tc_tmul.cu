@@ -14,7 +14,10 @@
 //
 //   warp 0     TMA producer      warp 1  MMA issuer (.ts)      warp 2  TMEM allocation
 //   warps 4-7  transpose + split: smem -> TMEM (hi | lo)       warps 8-15  epilogue (column halves)
+#include <stdlib.h>
 #include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -176,7 +179,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       tc_fence_after();
       float* og = a.out + (size_t)g * a.sOg + (size_t)nt * 128 + n_in_tile;
       const int mh = round_up_dev((MT + 1) / 2, 32);  // this warp's rows: [eh*mh, min(MT, eh*mh + mh))
-      for (int c0 = eh * mh; c0 < min(MT, eh * mh + mh); c0 += 32) {
+      const int c_end = min(MT, eh * mh + mh);
+      if (eh * mh >= c_end) {  // this warp has no rows of the tile (MT <= 32): it still owes its arrival
+        tc_fence_before();
+        mbar_arrive(&acc_empty[ab]);
+      }
+      for (int c0 = eh * mh; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(T_ACC + ab * 128 + lane_addr + c0, v);
         if (MT <= 64) {  // + the low-order accumulator
@@ -187,24 +195,38 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
         }
         tmem_ld_wait();
+        if (c0 + 32 >= c_end) {  // last read of this accumulator by this warp: the MMA warp may reuse it while we store
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+        }
+        // output row address of m: (m / mdiv) * sOm + (m % mdiv) * sOmLo.  mdiv is 1 (plain rows) or 2 (the (h, ri)
+        // rows of the inverse-H output) in every plan: a run-time division per element made this loop the kernel's
+        // critical path for many-row outputs, so the two cases are spelled out
+        const int m0 = mt * MT + c0, nrow = min(min(32, c_end - c0), a.M - m0);
+        auto store_rows = [&](auto MD) {
+          constexpr int md = decltype(MD)::value;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = mt * MT + c0 + i;
-          if (c0 + i < min(MT, eh * mh + mh) && m < a.M) {
-            float* dst = og + (size_t)(m / a.mdiv) * a.sOm + (size_t)(m % a.mdiv) * a.sOmLo;
-            const float x = __uint_as_float(v[i]);
-            if (a.split_off) {
-              const float hi = tf32_hi(x);
-              dst[0] = hi;
-              dst[a.split_off] = x - hi;
-            } else {
-              dst[0] = x;
+          for (int i = 0; i < 32; ++i) {
+            if (i < nrow) {
+              const int m = m0 + i;
+              const size_t off = md == 1 ? (size_t)m * a.sOm
+                                 : md == 2 ? (size_t)(m >> 1) * a.sOm + (size_t)(m & 1) * a.sOmLo
+                                           : (size_t)(m / a.mdiv) * a.sOm + (size_t)(m % a.mdiv) * a.sOmLo;
+              const float x = __uint_as_float(v[i]);
+              if (a.split_off) {
+                const float hi = tf32_hi(x);
+                og[off] = hi;
+                og[off + a.split_off] = x - hi;
+              } else {
+                og[off] = x;
+              }
             }
           }
-        }
+        };
+        if (a.mdiv == 1) store_rows(std::integral_constant<int, 1>{});
+        else if (a.mdiv == 2) store_rows(std::integral_constant<int, 2>{});
+        else store_rows(std::integral_constant<int, 0>{});
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
     }
   }
   tc_fence_before();
@@ -220,9 +242,14 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
   // Measured on B200: the transposed scheme wins for long contractions with few output rows (forward H: 25 ->
   // 19 us at C2, 8.9 -> 5.7 ms per rollout in 3-D) and loses for the short-K inverse transforms, where a work
   // item is a single chunk and the streamed table outweighs the data; those stay on the FFMA kernel.
-  // (round 2, measured again with 128-row m tiles available: short-K inverse H on this kernel - C2: 2.0 -> 3.15 ms per
-  // rollout, 3-D cylinder: 10.1 -> 19.1 ms - still loses; K <= 64 stays on the FFMA kernel.)
-  if (N % 128 != 0 || M < 1 || M > 1024 || K <= TM_CH) return 0;
+  // Short contractions (K <= 64: a work item is a single chunk): every m tile re-stages the same data tile, so the
+  // tensor-core kernel wins only with at most two m tiles (3-D inverse H, 2 * H' = 140 rows: 10.3 -> 9.2 ms per cylinder
+  // rollout) and loses with more (C2 inverse H, 524 rows = 5 tiles: 1.96 -> 2.47 ms); B200FNO_TMUL_SHORTK=0|1 overrides.
+  {
+    const char* e = getenv("B200FNO_TMUL_SHORTK");
+    const bool shortk_ok = e ? atoi(e) != 0 : (M > 128 && M <= 256);
+    if (N % 128 != 0 || M < 1 || M > 1024 || (K <= TM_CH && !shortk_ok)) return 0;
+  }
   // m tiles: as few as fit 128 accumulator columns, rows balanced over them (M = 140 -> 2 x 80, not 128 + 12)
   const int n_mt0 = ceil_div(M, 128);
   const int MT = round_up(ceil_div(M, n_mt0), 16);
