@@ -260,7 +260,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   {  // forward H: g=(b,t): [2KH x 2Hp] . [2Hp x m3*Cp]
     StageScope sc(tm, ST_FWD_H, st);
     float* fwdH_out = g.ndim == 3 ? bufBC : bufS;
-    if (tmR4 && tab.tm_fwdH.ok)
+    if (tmR4 && tmul_use(tab.tm_fwdH, B * g.Tp))
       B2_TRY(launch_tmul_tc(tab.tm_fwdH, tmR4[0], fwdH_out, B * g.Tp, 2LL * g.KH * n_hw, n_hw, 1, 0, 0, st));
     else
       B2_TRY(launch_lmul(tab.LH, tab.ldLH, 2 * g.KH, 2 * g.Hp, bufA, (long long)g.Hp * 2 * n_hw, n_hw, fwdH_out,
@@ -269,7 +269,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   if (g.ndim == 3) {
     StageScope sc(tm, ST_FWD_T, st);
     const long long n_t = (long long)g.KH * n_hw;
-    if (tmR4 && tab.tm_fwdT.ok)
+    if (tmR4 && tmul_use(tab.tm_fwdT, B))
       B2_TRY(launch_tmul_tc(tab.tm_fwdT, tmR4[1], bufS, B, 2LL * g.KT * n_t, n_t, 1, 0, 0, st));
     else
       B2_TRY(launch_lmul(tab.LT, tab.ldLT, 2 * g.KT, 2 * g.Tp, bufBC, (long long)g.Tp * 2 * n_t, n_t, bufS,
@@ -286,7 +286,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
   if (g.ndim == 3) {
     StageScope sc(tm, ST_INV_T, st);
     const long long n_t = (long long)g.KH * n_hw;
-    if (tmR4 && tab.tm_invT.ok)
+    if (tmR4 && tmul_use(tab.tm_invT, B))
       B2_TRY(launch_tmul_tc(tab.tm_invT, tmR4[2], bufBC, B, (long long)g.Tp * 2 * n_t, n_t, 1, 0, 0, st));
     else
       B2_TRY(launch_lmul(tab.LTi, tab.ldLTi, 2 * g.Tp, 2 * g.KT, bufO, 2LL * g.KT * n_t, n_t, bufBC,
@@ -298,7 +298,7 @@ static int run_spectral(const Geom& g, const Tables& tab, int B, const float* ac
     if (tc_planes) {
       // D[row=(g,h)][hl][k=(ri,kw)][o]: m = h*2+ri -> h * (2*K2p*Cp) + ri * (m3*Cp); lo plane at +K2p*Cp
       const long long plane = (long long)g.K2p * g.Cp;
-      if (tmR4 && tab.tm_invH.ok)
+      if (tmR4 && tmul_use(tab.tm_invH, B * g.Tp))
         B2_TRY(launch_tmul_tc(tab.tm_invH, tmR4[3], bufAD, B * g.Tp, (long long)g.Hp * 2 * plane, 2 * plane, 2, n_hw,
                               plane, st));
       else
@@ -1114,11 +1114,11 @@ int b200fno_plan_stage_impl(const b200fno_plan_t* p, int32_t stage) {
   switch (stage) {
     case ST_LIFT: return p->use_tc_lift;
     case ST_FWD_W: return p->use_tc && p->use_tc_fwdw;  // (tb below: the H / T plans of slice 0 when the plan is split)
-    case ST_FWD_H: return p->use_tc && p->use_tc_tmul && tb.tm_fwdH.ok;
-    case ST_FWD_T: return p->use_tc && p->use_tc_tmul && tb.tm_fwdT.ok;
+    case ST_FWD_H: return p->use_tc && p->use_tc_tmul && tmul_use(tb.tm_fwdH, p->d.max_batch * p->g.Tp);
+    case ST_FWD_T: return p->use_tc && p->use_tc_tmul && tmul_use(tb.tm_fwdT, p->d.max_batch);
     case ST_MODES: return p->use_tc_modes;
-    case ST_INV_T: return p->use_tc && p->use_tc_tmul && tb.tm_invT.ok;
-    case ST_INV_H: return p->use_tc && p->use_tc_tmul && tb.tm_invH.ok;
+    case ST_INV_T: return p->use_tc && p->use_tc_tmul && tmul_use(tb.tm_invT, p->d.max_batch);
+    case ST_INV_H: return p->use_tc && p->use_tc_tmul && tmul_use(tb.tm_invH, p->d.max_batch * p->g.Tp);
     case ST_LAYER: return p->use_tc;
     case ST_PROJ: return p->use_tc_proj;
   }

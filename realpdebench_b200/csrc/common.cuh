@@ -103,6 +103,9 @@ struct TmulPlan {
 };
 int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, int K, int N);
 void tmul_plan_free(TmulPlan* tp);
+// Is the tensor-core kernel the better choice for G groups?  A single-chunk plan (K <= 64) runs one (g, column tile) unit
+// per CTA: it needs enough units to fill the GPU (C2 inverse H, 64 units: 1.96 ms on FFMA vs 3.3 ms; C4, 560 units: 5.1 -> 3.0)
+bool tmul_use(const TmulPlan& tp, int G);
 int tmul_make_data_map(CUtensorMap* m, const float* R, int G, int K, int N, long long strideRg);
 int launch_tmul_tc(const TmulPlan& tp, const CUtensorMap& tmR, float* out, int G, long long sOg, long long sOm,
                    int mdiv, long long sOmLo, long long split_off, cudaStream_t st);

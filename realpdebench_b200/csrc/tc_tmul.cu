@@ -32,6 +32,8 @@ constexpr int TM_XS = 32768;   // data part of a stage: 4 quarters x 64 k x 128 
 struct TmulArgs {
   float* out;
   int G, NT, n_mt, MT, M, nchunk, Mpad, NS, stage_bytes;  // NT = N/128 column tiles, MT rows per m tile
+  int share;  // single-chunk contraction with several m tiles: the data tile is staged ONCE per (g, column tile) and
+              // every m tile multiplies it (work unit = (g, nt), inner loop over m tiles)
   long long sOg, sOm, sOmLo, split_off;
   int mdiv;
 };
@@ -48,7 +50,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = a.MT, nchunk = a.nchunk, NS = a.NS, SB = a.stage_bytes;
   const int n_items = a.G * a.NT * a.n_mt;
-  const int n_my = (int)blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const bool share = a.share != 0;
+  const int n_units = a.G * a.NT;  // share mode: (g, nt) units, a.n_mt accumulator-level items each
+  const int n_my_u = (int)blockIdx.x < n_units ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int n_my = share ? n_my_u * a.n_mt
+                         : ((int)blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 5);
@@ -68,6 +74,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
   pdl_wait();  // everything below may touch the previous kernel's output (PDL, common.cuh)
 
   auto decode = [&](int ip, int& g, int& nt, int& mt) {
+    if (share) {  // item ip of this CTA = m tile (ip % n_mt) of its unit (ip / n_mt)
+      const int wu = blockIdx.x + (ip / a.n_mt) * gridDim.x;
+      mt = ip % a.n_mt, nt = wu % a.NT, g = wu / a.NT;
+      return;
+    }
     const int wi = blockIdx.x + ip * gridDim.x;  // m tile fastest: the data tile is re-read from L2
     mt = wi % a.n_mt;
     nt = (wi / a.n_mt) % a.NT;
@@ -83,10 +94,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
         mbar_wait(&x_empty[sx], px ^ 1);
         if (elect_one_sync()) {
           uint8_t* st = smem + sx * SB;
-          mbar_arrive_expect_tx(&x_full[sx], (uint32_t)(TM_XS + 4 * MT * 128));
+          const bool with_data = !share || mt == 0;  // share mode: only the first m tile of a unit carries the data
+          mbar_arrive_expect_tx(&x_full[sx], (uint32_t)((with_data ? TM_XS : 0) + 4 * MT * 128));
           // data: columns n = nt*128 + q*32 + lane; viewed as [g][k][nb = n/64][c = n%64], box (32 c, 64 k, 2 nb)
-          tma_load_4d(st, &tmR, &x_full[sx], 0, ch * TM_CH, 2 * nt, g);
-          tma_load_4d(st + 16384, &tmR, &x_full[sx], 32, ch * TM_CH, 2 * nt, g);
+          if (with_data) tma_load_4d(st, &tmR, &x_full[sx], 0, ch * TM_CH, 2 * nt, g);
+          if (with_data) tma_load_4d(st + 16384, &tmR, &x_full[sx], 32, ch * TM_CH, 2 * nt, g);
           for (int hl = 0; hl < 2; ++hl)
             for (int s = 0; s < 2; ++s)
               tma_load_2d(st + TM_XS + (hl * 2 + s) * MT * 128, &tmL, &x_full[sx], 32 * (2 * ch + s),
@@ -103,9 +115,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
       const int ab = ip & 1, pab = (ip >> 1) & 1;
       mbar_wait(&acc_empty[ab], pab ^ 1);
       for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
-        const int t = cc & 1, pt = (cc >> 1) & 1;
+        // A buffer: one per chunk; in share mode one per UNIT (n_mt consecutive items use the same staged data)
+        const int ca = share ? ip / a.n_mt : cc, t = ca & 1, pt = (ca >> 1) & 1;
+        const bool first_of_a = !share || ip % a.n_mt == 0, last_of_a = !share || ip % a.n_mt == a.n_mt - 1;
         mbar_wait(&x_full[sx], px);
-        mbar_wait(&a_full[t], pt);
+        if (first_of_a) mbar_wait(&a_full[t], pt);
         tc_fence_after();
         // m tiles of at most 64 rows keep the low-order cross terms in their own accumulator (columns 64.. of the
         // slot): the tensor core's adder truncates, see tc_fwdw.cu
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
           for (int ks = 0; ks < 8; ++ks)
             umma_tf32_ts(acc, Ahi + ks * 8, dL_hi + (uint64_t)(ks >> 2) * sub + (uint64_t)((ks & 3) * 2), idesc,
                          MT <= 64 ? (ch | ks) != 0 : 1);
-          umma_commit(&a_empty[t]);
+          if (last_of_a) umma_commit(&a_empty[t]);
           umma_commit(&x_empty[sx]);
           if (ch == nchunk - 1) umma_commit(&acc_full[ab]);
         }
@@ -139,8 +153,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1)
     int cc = 0, sx = 0, px = 0;
     for (int ip = 0; ip < n_my; ++ip) {
       for (int ch = 0; ch < nchunk; ++ch, ++cc, sx = (sx + 1 == NS ? 0 : sx + 1), px ^= (sx == 0)) {
-        const int t = cc & 1, pt = (cc >> 1) & 1;
+        const int ca = share ? ip / a.n_mt : cc, t = ca & 1, pt = (ca >> 1) & 1;
         mbar_wait(&x_full[sx], px);
+        if (share && ip % a.n_mt != 0) {  // a later m tile of the unit: nothing to stage, the stage still needs our arrival
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_empty[sx]);
+          continue;
+        }
         mbar_wait(&a_empty[t], pt ^ 1);
         tc_fence_after();
         const uint32_t src = smem_u32(smem) + sx * SB + col_base;
@@ -247,7 +266,7 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
   // rollout) and loses with more (C2 inverse H, 524 rows = 5 tiles: 1.96 -> 2.47 ms); B200FNO_TMUL_SHORTK=0|1 overrides.
   {
     const char* e = getenv("B200FNO_TMUL_SHORTK");
-    const bool shortk_ok = e ? atoi(e) != 0 : (M > 128 && M <= 256);
+    const bool shortk_ok = e ? atoi(e) != 0 : M > 128;
     if (N % 128 != 0 || M < 1 || M > 1024 || (K <= TM_CH && !shortk_ok)) return 0;
   }
   // m tiles: as few as fit 128 accumulator columns, rows balanced over them (M = 140 -> 2 x 80, not 128 + 12)
@@ -279,6 +298,11 @@ int tmul_plan_build(TmulPlan* tp, const std::vector<float>& L, int ldl, int M, i
   tp->ok = true;
   return 0;
 }
+bool tmul_use(const TmulPlan& tp, int G) {
+  if (!tp.ok) return false;
+  if (tp.nchunk > 1) return true;
+  return (long long)G * (tp.N / 128) >= 2 * 148;
+}
 void tmul_plan_free(TmulPlan* tp) {
   if (tp->table) cudaFree(tp->table);
   tp->table = nullptr, tp->ok = false;
@@ -298,7 +322,8 @@ int launch_tmul_tc(const TmulPlan& tp, const CUtensorMap& tmR, float* out, int G
   a.out = out, a.G = G, a.NT = tp.N / 128, a.n_mt = tp.n_mt, a.MT = tp.MT, a.M = tp.M, a.nchunk = tp.nchunk;
   a.Mpad = tp.Mpad, a.NS = tp.NS, a.stage_bytes = tp.stage_bytes;
   a.sOg = sOg, a.sOm = sOm, a.sOmLo = sOmLo, a.split_off = split_off, a.mdiv = mdiv;
-  const int items = G * a.NT * a.n_mt;
+  a.share = (tp.nchunk == 1 && tp.n_mt > 1 && getenv("B200FNO_TMUL_NO_SHARE") == nullptr) ? 1 : 0;
+  const int items = a.share ? G * a.NT : G * a.NT * a.n_mt;
   const int smem = tp.NS * tp.stage_bytes + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_tmul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   B2_CUDA(launch_kernel(tc_tmul_kernel, dim3(std::min(148, items)), dim3(TM_THREADS), (size_t)smem, st, a, tmR, tp.tmL));
