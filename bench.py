@@ -439,7 +439,9 @@ def main():
     ap.add_argument("--engine-impl", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--batch", type=int, default=0, help="override batch per GPU (not the headline config)")
     ap.add_argument("--n-auto", type=int, default=0, help="override rollout length (not the headline config)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10,
+                    help="steps of the end-to-end arm (a three-stage copy / compute / copy pipeline: its fill and drain "
+                         "cost two transfer periods, 40 %% of a 5-step run and 20 %% of a 10-step one)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="f32 = the headline (3xTF32, 1e-5 parity); bf16 = the reference's torch.autocast(bfloat16) "
                          "arithmetic on the engine (Linear / Conv operands in bf16, spectral stages fp32; 1e-2 parity)")
