@@ -49,6 +49,7 @@ class FNOEngine:
         if self._plan is not None:
             _capi.lib().b200fno_plan_destroy(self._plan)
         self._plan, self._ws, self._weights_key, self._train_ws = None, None, None, None
+        self.__dict__.pop("_graphs", None)  # captured rollouts hold the old plan's addresses
 
     def __del__(self):  # pragma: no cover - interpreter shutdown order
         try:
@@ -156,9 +157,16 @@ class FNOEngine:
         return y
 
     def rollout(self, x0: torch.Tensor, a: torch.Tensor, b: torch.Tensor, n_steps: int, sd: dict, key,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, graph: bool = False) -> torch.Tensor:
         """x0: normalised input [B,T,H,W,C_in]; a, b: per-output-channel affine (len C_out).
-        Returns cat(preds[1:], dim=1)[..., :C_out] of eval.py:313-322, shape [B, n*T_out, H, W, C_out]."""
+        Returns cat(preds[1:], dim=1)[..., :C_out] of eval.py:313-322, shape [B, n*T_out, H, W, C_out].
+
+        ``graph=True``: the ~22-30 launches per step are captured ONCE per (batch, n_steps) into a CUDA graph and
+        replayed (small batches are launch-latency bound).  The graph owns static input / affine / output buffers:
+        the returned tensor is that static output (valid until the next graph rollout of the same shape) unless
+        ``out`` is given, in which case the result is copied into it."""
+        if graph:
+            return self._rollout_graph(x0, a, b, n_steps, sd, key, out)
         _require_cuda(x0, "input")
         if tuple(x0.shape[1:]) != self.shape_in:
             raise RuntimeError(f"b200fno: input shape {tuple(x0.shape)} does not match [B,{self.shape_in}]")
@@ -178,6 +186,38 @@ class FNOEngine:
                                               state.data_ptr() if state is not None else None, out.data_ptr(),
                                               stream))
         return out
+
+    def _rollout_graph(self, x0, a, b, n_steps, sd, key, out):
+        _require_cuda(x0, "input")
+        B = x0.shape[0]
+        self.prepare(B, x0.device, sd, key)  # plan + packed weights OUTSIDE the capture (a re-pack keeps its addresses)
+        gkey = (B, n_steps, self.compute, id(self._plan))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(gkey)
+        if g is None:
+            t_out, h, w, c_out = self.shape_out
+            st = {"x": torch.empty_like(x0, memory_format=torch.contiguous_format),
+                  "a": torch.empty(c_out, dtype=torch.float32, device=x0.device),
+                  "b": torch.empty(c_out, dtype=torch.float32, device=x0.device),
+                  "out": torch.empty((B, n_steps * t_out, h, w, c_out), dtype=torch.float32, device=x0.device)}
+            st["x"].copy_(x0), st["a"].copy_(a), st["b"].copy_(b)
+            side = torch.cuda.Stream(device=x0.device)
+            side.wait_stream(torch.cuda.current_stream(x0.device))
+            with torch.cuda.stream(side):  # warm-up on the capture stream (lazy module loading must not be captured)
+                self.rollout(st["x"], st["a"], st["b"], n_steps, sd, key, out=st["out"])
+            torch.cuda.current_stream(x0.device).wait_stream(side)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                # the state ping-pong buffer is allocated inside the capture: it lives in the graph's private pool
+                self.rollout(st["x"], st["a"], st["b"], n_steps, sd, key, out=st["out"])
+            g = graphs[gkey] = (cg, st)
+        cg, st = g
+        st["x"].copy_(x0), st["a"].copy_(a.to(st["a"].device, torch.float32)), st["b"].copy_(b.to(st["b"].device, torch.float32))
+        cg.replay()
+        if out is not None:
+            out.copy_(st["out"])
+            return out
+        return st["out"]
 
     # -- training path ----------------------------------------------------------
     def _ensure_train_ws(self, device: torch.device):

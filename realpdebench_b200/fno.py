@@ -161,12 +161,13 @@ class _EngineFNO(Model):
         names = [k for k, _ in self.named_parameters()]
         return _TrainForward.apply(self, x, names, *[sd[k] for k in names])
 
-    def rollout(self, x0, affine_a, affine_b, n_steps, out=None):
-        """Fused eval.py:313-321 loop; see realpdebench_b200.rollout for the full per-batch protocol."""
+    def rollout(self, x0, affine_a, affine_b, n_steps, out=None, graph=False):
+        """Fused eval.py:313-321 loop; see realpdebench_b200.rollout for the full per-batch protocol.
+        ``graph=True`` replays a CUDA graph captured once per (batch, n_steps) (FNOEngine.rollout)."""
         self._check_eval()
         sd, key = self._engine_state()
         self._engine.set_compute(self._resolve_compute()[0])
-        return self._engine.rollout(x0, affine_a, affine_b, n_steps, sd, key, out=out)
+        return self._engine.rollout(x0, affine_a, affine_b, n_steps, sd, key, out=out, graph=graph)
 
     def train_loss(self, input, target):
         pred = self(input)  # fno.py:131-133

@@ -362,3 +362,26 @@ def test_rollout_is_graph_capturable(R, golden):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_rollout_graph_option_replays_for_new_inputs(R):
+    """``model.rollout(..., graph=True)``: captured once per (batch, n_steps), replayed with the caller's new input and
+    affine copied into the graph's static buffers; bit-identical to the eager launches (width 64: tcgen05 kernels)."""
+    torch.manual_seed(91)
+    s = (4, 40, 100, 3)
+    sd = O.init_state(2, (6, 8), 3, 64, s, s)
+    O.randomize_bn(sd, 92)
+    m = R.FNO2d(6, 8, 3, 64, s, s)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    a = torch.tensor([1.5, 0.5, 2.0], device=dev())
+    b = torch.tensor([0.1, -0.2, 0.3], device=dev())
+    for seed in (1, 2, 3):
+        torch.manual_seed(seed)
+        x0 = torch.randn(2, *s, device=dev())
+        eager = m.rollout(x0, a * seed, b, 3)
+        got = m.rollout(x0, a * seed, b, 3, graph=True)
+        assert torch.equal(got, eager), seed
+    out = torch.empty_like(eager)
+    assert m.rollout(x0, a * 3, b, 3, out=out, graph=True) is out and torch.equal(out, eager)
+    assert len(m.engine._graphs) == 1
