@@ -243,3 +243,25 @@ def test_bench_loss_check_fixture_matches_bench_workload():
     ndim, modes, L, width, s_in, s_out, B, n_auto = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
     assert ref is not None and ref["batch"] == B and ref["n_autoregressive"] == n_auto and ref["seed"] == 1234
     assert abs(ref["normalized_loss"] - sum(ref["per_sample"]) / B) < 1e-12
+
+
+def test_compute_mode_selection_follows_autocast_and_rejects_unknown_modes():
+    """Host logic of the bf16 mode: an active CUDA bf16 autocast context selects it, ``set_compute`` validates
+    its argument and survives ``set_impl``; no device needed (the plan is only created on the first CUDA call)."""
+    import realpdebench_b200 as R
+    m = R.FNO2d(3, 4, 2, 16, (2, 8, 8, 2), (2, 8, 8, 2))
+    assert m._resolve_compute() == ("f32", False) and m.engine.compute == "f32"
+    if torch.cuda.is_available():  # torch disables a CUDA autocast context on a box without CUDA (covered by -m gpu)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert m._resolve_compute() == ("bf16", True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            assert m._resolve_compute() == ("f32", False)  # only bf16 autocast has an engine mode
+    m.set_compute("bf16")
+    assert m._resolve_compute() == ("bf16", False) and m.engine.compute == "bf16"
+    m.set_impl("simt")
+    assert m.engine.compute == "bf16"  # a rebuilt engine keeps the mode
+    with pytest.raises(ValueError, match="compute must be one of"):
+        m.set_compute("fp8")
+    from realpdebench_b200 import _capi
+    lib = _capi.lib()
+    assert lib.b200fno_plan_set_compute(None, 1) != 0 and "compute" in lib.b200fno_last_error().decode()
