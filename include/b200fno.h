@@ -275,6 +275,11 @@ int b200fno_selftest_mma_rate(int32_t N, int32_t iters, int32_t a_in_tmem, int32
  * may be NULL).  Returns the table length in floats or a negative error code. */
 int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
                            int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t, int32_t* freqs_h);
+/* The same for one W-mode slice [kw0, kw0 + m3) - the tables a plan builds per slice when modes3 in (32, 64] runs as two
+ * slices on the tensor-core kernels (the W tables carry the frequency offset, the H / T tables are unchanged). */
+int64_t b200fno_host_table_slice(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
+                                 int32_t kw0, int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t,
+                                 int32_t* freqs_h);
 /* Which kernel family stage `stage` (order of b200fno_timing_collect) resolves to after b200fno_plan_bind:
  * 1 = tcgen05 tensor-core kernel, 0 = fp32 FFMA kernel, negative = error.  Lets tests and bench.py state
  * which path produced a number. */

@@ -21,7 +21,7 @@ SYMBOLS = (
     "b200fno_plan_bind", "b200fno_pack_weights", "b200fno_forward", "b200fno_rollout",
     "b200fno_spectral_workspace_bytes", "b200fno_spectral_conv", "b200fno_launch_count",
     "b200fno_debug_first_nonfinite", "b200fno_spectral_cache_clear",
-    "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
+    "b200fno_launch_count_reset", "b200fno_host_table", "b200fno_host_table_slice", "b200fno_algorithmic_bytes", "b200fno_timing_enable",
     "b200fno_timing_collect", "b200fno_selftest_umma", "b200fno_selftest_mma_rate",
     "b200fno_train_workspace_bytes", "b200fno_train_bind", "b200fno_train_forward", "b200fno_train_backward",
     "b200fno_adam_step", "b200fno_metrics_workspace_bytes", "b200fno_eval_metrics", "b200fno_plan_stage_impl",
@@ -109,6 +109,9 @@ def lib() -> C.CDLL:
     L.b200fno_host_table.restype = i64
     L.b200fno_host_table.argtypes = [i32] * 8 + [C.POINTER(C.c_float), i64, C.POINTER(i32), C.POINTER(i32),
                                                  C.POINTER(i32)]
+    L.b200fno_host_table_slice.restype = i64
+    L.b200fno_host_table_slice.argtypes = [i32] * 9 + [C.POINTER(C.c_float), i64, C.POINTER(i32), C.POINTER(i32),
+                                                       C.POINTER(i32)]
     L.b200fno_timing_enable.restype = C.c_int
     L.b200fno_timing_enable.argtypes = [vp, C.c_int]
     L.b200fno_timing_collect.restype = C.c_int
@@ -154,19 +157,20 @@ def ptr_array(ptrs):
     return arr
 
 
-def host_table(ndim, t, h, w, m1, m2, m3, which):
-    """numpy copy of a truncated-DFT table + (ld, kept T freqs, kept H freqs)."""
+def host_table(ndim, t, h, w, m1, m2, m3, which, kw0=0):
+    """numpy copy of a truncated-DFT table + (ld, kept T freqs, kept H freqs); ``kw0``: first W frequency of a mode
+    slice of ``m3`` frequencies (b200fno_host_table_slice)."""
     import numpy as np
     L = lib()
     ld = C.c_int32(0)
     ft = (C.c_int32 * max(t, 1))()
     fh = (C.c_int32 * max(h, 1))()
-    n = L.b200fno_host_table(ndim, t, h, w, m1, m2, m3, which, None, 0, C.byref(ld), ft, fh)
+    n = L.b200fno_host_table_slice(ndim, t, h, w, m1, m2, m3, kw0, which, None, 0, C.byref(ld), ft, fh)
     if n < 0:
         check(int(n))
     buf = np.zeros(int(n), dtype=np.float32)
-    L.b200fno_host_table(ndim, t, h, w, m1, m2, m3, which, buf.ctypes.data_as(C.POINTER(C.c_float)), n,
-                         C.byref(ld), ft, fh)
+    L.b200fno_host_table_slice(ndim, t, h, w, m1, m2, m3, kw0, which, buf.ctypes.data_as(C.POINTER(C.c_float)), n,
+                               C.byref(ld), ft, fh)
     kt = min(2 * m1, t) if ndim == 3 else 1
     kh = min(2 * m2, h)
     return buf.reshape(-1, ld.value), list(ft[:kt]), list(fh[:kh])

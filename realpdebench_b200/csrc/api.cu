@@ -1087,15 +1087,22 @@ int b200fno_timing_collect(b200fno_plan_t* p, double* ms, int64_t* count) {
 
 int64_t b200fno_host_table(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
                            int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t, int32_t* freqs_h) {
-  if ((ndim != 2 && ndim != 3) || which < 0 || which > 5) {
+  return b200fno_host_table_slice(ndim, t, h, w, m1, m2, m3, 0, which, out, cap, ld, freqs_t, freqs_h);
+}
+
+int64_t b200fno_host_table_slice(int32_t ndim, int32_t t, int32_t h, int32_t w, int32_t m1, int32_t m2, int32_t m3,
+                                 int32_t kw0, int32_t which, float* out, int64_t cap, int32_t* ld, int32_t* freqs_t,
+                                 int32_t* freqs_h) {
+  if ((ndim != 2 && ndim != 3) || which < 0 || which > 5 || kw0 < 0) {
     set_error("bad argument");
     return B200FNO_EINVAL;
   }
   Geom g;
-  B2_TRY(make_geom(ndim, t, h, w, 4, m1, m2, m3, &g));
+  B2_TRY(make_geom(ndim, t, h, w, 4, m1, m2, kw0 + m3, &g));  // the LAST kept frequency must fit the grid
+  g.m3 = m3, g.K2 = 2 * m3, g.K2p = round_up(g.K2, 4), g.NM = g.KT * g.KH * m3;
   Tables tab;
   std::vector<float> host[6];
-  B2_TRY(compute_tables_host(g, m1, m2, &tab, host));
+  B2_TRY(compute_tables_host(g, m1, m2, &tab, host, kw0));
   const int lds[6] = {tab.ldLF, tab.ldLH, tab.ldLT, tab.ldLTi, tab.ldLHi, g.K2p};
   if (ld) *ld = lds[which];
   if (freqs_t) std::copy(tab.ft.begin(), tab.ft.end(), freqs_t);

@@ -9,13 +9,15 @@ from oracle import fno_oracle as O
 from realpdebench_b200 import _capi
 
 
-def emulate_spectral(ndim, x, weights, m1, m2, m3):
-    """x: [B,Ci,(T,)H,W] float64 numpy; weights: list of complex corner arrays.  Mirrors api.cu:run_spectral."""
+def emulate_spectral(ndim, x, weights, m1, m2, m3, kw0=0):
+    """x: [B,Ci,(T,)H,W] float64 numpy; weights: list of complex corner arrays.  Mirrors api.cu:run_spectral.
+    ``kw0``: the mode slice [kw0, kw0 + m3) of a plan that splits modes3 (api.cu: ModeSlice); ``weights`` then hold that
+    slice of the W modes."""
     if ndim == 2:
         x = x[:, :, None]
     B, Ci, T, H, W = x.shape
     Co = weights[0].shape[1]
-    tabs = [_capi.host_table(ndim, T, H, W, m1, m2, m3, k) for k in range(6)]
+    tabs = [_capi.host_table(ndim, T, H, W, m1, m2, m3, k, kw0) for k in range(6)]
     (LF, ft, fh), LH, LT, LTi, LHi, Gt = tabs[0], tabs[1][0], tabs[2][0], tabs[3][0], tabs[4][0], tabs[5][0]
     KT, KH = len(ft), len(fh)
     act = np.transpose(x, (0, 2, 3, 4, 1))  # channels-last [B,T,H,W,C]
@@ -82,4 +84,23 @@ def test_2d_stage_sequence_matches_oracle(shape, modes):
     ws = [torch.randn(3, 4, m2, m3, dtype=torch.cdouble) for _ in range(2)]
     ref = O.spectral_conv2d(x, *ws)
     got = emulate_spectral(2, x.numpy(), [w.numpy() for w in ws], 1, m2, m3)
+    assert O.rel_l2(torch.from_numpy(got), ref) < 5e-7
+
+
+@pytest.mark.parametrize("ndim,shape,modes", [(2, (30, 132), (6, 48)), (2, (22, 130), (5, 64)), (3, (8, 10, 100), (2, 3, 48))])
+def test_two_mode_slices_add_up_to_the_full_operator(ndim, shape, modes):
+    """modes3 in (32, 64] runs as two W-mode slices (api.cu: ModeSlice): slice s uses DFT tables with the frequency offset
+    kw0 = s * m3 / 2 and the weights' W modes [kw0, kw0 + m3/2); the inverse-W terms of the two slices add.  Emulated here
+    with the library's own slice tables (b200fno_host_table_slice) against the oracle's full SpectralConv."""
+    torch.manual_seed(4)
+    m3 = modes[-1]
+    ci, co = 3, 4
+    x = torch.randn(2, ci, *shape, dtype=torch.float64)
+    ncorner = 4 if ndim == 3 else 2
+    ws = [torch.randn(ci, co, *modes, dtype=torch.cdouble) for _ in range(ncorner)]
+    ref = (O.spectral_conv3d if ndim == 3 else O.spectral_conv2d)(x, *ws)
+    m1, m2 = (modes[0], modes[1]) if ndim == 3 else (1, modes[0])
+    half = m3 // 2
+    got = sum(emulate_spectral(ndim, x.numpy(), [w[..., s * half:(s + 1) * half].numpy() for w in ws], m1, m2, half,
+                               kw0=s * half) for s in range(2))
     assert O.rel_l2(torch.from_numpy(got), ref) < 5e-7
