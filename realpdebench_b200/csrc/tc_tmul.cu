@@ -322,7 +322,8 @@ int launch_tmul_tc(const TmulPlan& tp, const CUtensorMap& tmR, float* out, int G
   a.out = out, a.G = G, a.NT = tp.N / 128, a.n_mt = tp.n_mt, a.MT = tp.MT, a.M = tp.M, a.nchunk = tp.nchunk;
   a.Mpad = tp.Mpad, a.NS = tp.NS, a.stage_bytes = tp.stage_bytes;
   a.sOg = sOg, a.sOm = sOm, a.sOmLo = sOmLo, a.split_off = split_off, a.mdiv = mdiv;
-  a.share = (tp.nchunk == 1 && tp.n_mt > 1 && getenv("B200FNO_TMUL_NO_SHARE") == nullptr) ? 1 : 0;
+  static const bool no_share = getenv("B200FNO_TMUL_NO_SHARE") != nullptr;  // read once, not per launch
+  a.share = (tp.nchunk == 1 && tp.n_mt > 1 && !no_share) ? 1 : 0;
   const int items = a.share ? G * a.NT : G * a.NT * a.n_mt;
   const int smem = tp.NS * tp.stage_bytes + 1024;
   B2_CUDA(cudaFuncSetAttribute(tc_tmul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
