@@ -104,9 +104,8 @@ __global__ void __launch_bounds__(MD_THREADS, 1)
       mbar_wait(&w_empty[s], ps ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&w_full[s], MD_WS);
-        // four boxes of 32 columns (128 B rows, the granularity the TMA streams best): stage = [column block][64 i][32]
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) tma_load_2d(sW + s * MD_WS + cb * 8192, &tmW, &w_full[s], 32 * cb, m * 64);
+        // ONE box = the mode's contiguous 32 KB block (64 rows of 512 B): a single sequential DRAM burst per mode
+        tma_load_2d(sW + s * MD_WS, &tmW, &w_full[s], 0, m * 64);
       }
       __syncwarp();
     }
@@ -148,14 +147,14 @@ __global__ void __launch_bounds__(MD_THREADS, 1)
       mbar_wait(&w_full[s], ps);
       mbar_wait(&a_empty[t], pt ^ 1);
       tc_fence_after();
-      // column (rw, o) = float L of a weight row = float `lane` of column block q: stage layout [4 blocks][64 i][32 floats]
-      const uint32_t src = smem_u32(sW) + s * MD_WS + (uint32_t)(q * 8192 + lane * 4);
+      // column (rw, o) = float L of a weight row: stage layout [64 i][128 floats] as in HBM
+      const uint32_t src = smem_u32(sW) + s * MD_WS + (uint32_t)(L * 4);
       const uint32_t Ahi = T_A + t * 128 + lane_addr, Alo = Ahi + 64;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32], hv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lds32(src + (uint32_t)((half * 32 + i) * 128));
+        for (int i = 0; i < 32; ++i) v[i] = lds32(src + (uint32_t)((half * 32 + i) * 512));
         if (half == 1) {  // the stage has been read completely
           __syncwarp();
           if (lane == 0) mbar_arrive(&w_empty[s]);
@@ -263,7 +262,7 @@ bool tc_modes_supported(const Geom& g, int B) { return g.Cp == 64 && B >= 1 && B
 int tc_make_modes_map(CUtensorMap* m, const float* Wpk, int NM) {
   uint64_t dims[2] = {128, (uint64_t)NM * 64};
   uint64_t strides[1] = {128 * 4};
-  uint32_t box[2] = {32, 64};
+  uint32_t box[2] = {128, 64};
   return encode_tensor_map(m, Wpk, 2, dims, strides, box, 0);
 }
 
