@@ -145,9 +145,10 @@ int b200fno_forward(b200fno_plan_t* plan, int32_t batch, const float* x, float* 
  * per-channel affine  p' = p * affine_a[c] + affine_b[c]  (SURVEY F6).
  *   x0    [batch][t_in][h][w][c_in]   normalised input (output of preprocess)
  *   pred  [batch][n_steps*t_out][h][w][c_out]  = torch.cat(preds[1:],1)[..., :c_out]
- *   state [2][batch][t_in][h][w][c_in] scratch for the fed-back inputs
- *         (may be NULL when n_steps == 1); parameter channels c_out..c_in-1
- *         are carried over from x0 (eval.py:317).
+ *   state [2][batch][t_in][h][w][c_in] scratch for the fed-back inputs when c_in > c_out: parameter channels
+ *         c_out..c_in-1 are carried over from x0 (eval.py:317).  May be NULL when n_steps == 1 or c_in == c_out:
+ *         without parameter channels step i + 1 reads its input straight from the prediction slice step i wrote
+ *         (the same tensor in eval.py:315-319), no state buffer and no second store exist.
  * n_steps > 1 requires t_out == t_in. */
 int b200fno_rollout(b200fno_plan_t* plan, int32_t batch, const float* x0, const float* affine_a,
                     const float* affine_b, int32_t n_steps, float* state, float* pred, void* stream);

@@ -783,7 +783,8 @@ static int run_proj(b200fno_plan* p, int B, const float* act, const ProjSpec& ps
 // so the forward-W kernel (and the projection) find their input in L2 and HBM sees the SURVEY 8d traffic: one read
 // and one write of the activation per layer.  The small L2-resident stages stay batch-wide (they are latency bound).
 // A and D live in separate buffers: fwdW_{l+1}(c) writes A while layer_l(c+1) still reads D.
-static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& ps, cudaStream_t st) {
+static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& ps, cudaStream_t st,
+                       long long x_sB = 0) {  // x_sB: element stride between the samples of x (0: contiguous samples)
   const Geom& g = p->g;
   const b200fno_desc_t& d = p->d;
   const int L = d.n_layers;
@@ -795,7 +796,8 @@ static int run_network(b200fno_plan* p, int B, const float* x, const ProjSpec& p
   Timing* tm = &p->timing;
   const long long rows_s = (long long)g.Tp * g.Hp;  // activation rows per sample
   const CUtensorMap tmR4[4] = {p->tmR_fwdH, p->tmR_fwdT, p->tmR_invT, p->tmR_invH};
-  const LiftArgs la = make_lift_args(p, B, x, p->act[0]);
+  LiftArgs la = make_lift_args(p, B, x, p->act[0]);
+  if (x_sB) la.x_sB = x_sB;
   if (p->split) {  // modes3 in (32, 64]: two mode slices per layer (struct ModeSlice); the layer output returns to
                    // the buffer its input came from, so `cur` never flips
     const Geom& gs = p->gs;
@@ -931,8 +933,14 @@ int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const flo
     set_error("null tensor or n_steps < 1");
     return B200FNO_EINVAL;
   }
-  if (n_steps > 1 && (d.t_out != d.t_in || !state)) {
-    set_error("n_steps > 1 needs t_out == t_in (got %d, %d) and a state buffer", d.t_out, d.t_in);
+  const long long HW0 = (long long)d.h * d.w;
+  // c_in == c_out: the next model input IS the prediction slice just written (eval.py:315-319: preds.append(p) holds the
+  // re-normalised prediction, and the same tensor is fed back), so the lift of step i + 1 reads it in place - sample
+  // stride n_steps * slice - and neither a state buffer nor its 252 MB store per step (C2) exist
+  const bool feed_from_pred = d.c_in == d.c_out && d.t_out == d.t_in && ((long long)d.t_out * HW0 * d.c_out) % 4 == 0 &&
+                              ((uintptr_t)pred & 15) == 0;
+  if (n_steps > 1 && (d.t_out != d.t_in || (!state && !feed_from_pred))) {
+    set_error("n_steps > 1 needs t_out == t_in (got %d, %d) and, with parameter channels, a state buffer", d.t_out, d.t_in);
     return B200FNO_EINVAL;
   }
   if (d.c_in < d.c_out) {
@@ -948,11 +956,17 @@ int b200fno_rollout(b200fno_plan_t* p, int32_t batch, const float* x0, const flo
     B2_TRY(launch_copy_params(x0, state, (long long)batch * d.t_in * HW, d.c_in, d.c_out, st));
   const float* cur = x0;
   for (int i = 0; i < n_steps; ++i) {
-    float* next = (i + 1 < n_steps) ? state + (size_t)(i & 1) * state_elems : nullptr;
     ProjSpec ps;
-    ps.aff_a = affine_a, ps.aff_b = affine_b, ps.out = pred + (size_t)i * step_elems, ps.out_sB = out_sB, ps.state = next;
-    B2_TRY(run_network(p, batch, cur, ps, st));
-    cur = next;
+    ps.aff_a = affine_a, ps.aff_b = affine_b, ps.out = pred + (size_t)i * step_elems, ps.out_sB = out_sB;
+    if (feed_from_pred) {
+      B2_TRY(run_network(p, batch, cur, ps, st, i == 0 ? 0 : out_sB));
+      cur = ps.out;
+    } else {
+      float* next = (i + 1 < n_steps) ? state + (size_t)(i & 1) * state_elems : nullptr;
+      ps.state = next;
+      B2_TRY(run_network(p, batch, cur, ps, st));
+      cur = next;
+    }
   }
   return 0;
 }

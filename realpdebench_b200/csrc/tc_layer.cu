@@ -503,7 +503,7 @@ int launch_lift_tc(const LiftArgs& la, const CUtensorMap& tmOut, const CUtensorM
       const int T_frames = la.x_sT ? la.T : NF;
       uint64_t dims[4] = {(uint64_t)la.W * la.c_in, (uint64_t)la.H, (uint64_t)T_frames, (uint64_t)la.B};
       uint64_t strides[3] = {(uint64_t)la.W * la.c_in * 4, (uint64_t)la.H * la.W * la.c_in * 4,
-                             (uint64_t)T_frames * la.H * la.W * la.c_in * 4};
+                             (uint64_t)la.x_sB * 4};  // samples need not be contiguous (rollout: slices of the prediction)
       uint32_t box[4] = {(uint32_t)IB, 1, (uint32_t)NF, 1};
       B2_TRY(encode_tensor_map(&tmIn, la.x, 4, dims, strides, box, 0));
       a.in_tma = 1, a.in_nb = nb, a.in_IB = IB, a.in_NF = NF, a.in_box_floats = box_floats;

@@ -180,7 +180,9 @@ class FNOEngine:
             raise RuntimeError("b200fno: affine vectors must have C_out entries")
         if out is None:
             out = torch.empty((B, n_steps * t_out, h, w, c_out), dtype=torch.float32, device=x0.device)
-        state = torch.empty((2, *x0.shape), dtype=torch.float32, device=x0.device) if n_steps > 1 else None
+        # c_in == c_out: the engine feeds each step from the prediction slice the previous one wrote (no state buffer)
+        need_state = n_steps > 1 and self.shape_in[3] != self.shape_out[3]
+        state = torch.empty((2, *x0.shape), dtype=torch.float32, device=x0.device) if need_state else None
         with torch.cuda.device(x0.device):
             check(_capi.lib().b200fno_rollout(self._plan, B, x0.data_ptr(), a.data_ptr(), b.data_ptr(), n_steps,
                                               state.data_ptr() if state is not None else None, out.data_ptr(),
